@@ -1,0 +1,89 @@
+"""Container-only loader for the UNMODIFIED reference (test infrastructure, never shipped).
+
+Imports `/root/reference/doppelspeller` read-only so the oracle restatement (`oracle/ds_oracle.c`,
+`oracle/oracle.py`) can be pinned against the reference's own numba kernels and so
+`tests/golden/make_golden.py` can mint golden vectors.  `/root/reference` does not exist on the GPU
+box: nothing under `tests/ -m gpu`, `bench.py` or `__graft_entry__.smoke()` may import this module.
+
+Shims needed:
+  * `Levenshtein` (python-levenshtein==0.12.0, requirements.txt:9) is not installed and
+    `doppelspeller/common.py:8` imports it at module import time -> a stub exposing `ratio`
+    backed by the restated InDel ratio (oracle.lev_ratio_float).
+  * `xgboost` (predict.py:6, train.py) is not installed -> empty stub module.
+  * `PROJECT_DATA_PATH` (settings.py:8-12) -> a temp dir with the gunzipped example CSVs.
+"""
+import gzip
+import os
+import shutil
+import sys
+import tempfile
+import types
+
+REFERENCE_ROOT = '/root/reference'
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, 'doppelspeller'))
+
+
+def _indel_ratio_py(a, b):
+    """ratio = (la + lb - indel) / (la + lb), 1.0 when both empty (python-levenshtein semantics)."""
+    la, lb = len(a), len(b)
+    if la + lb == 0:
+        return 1.0
+    prev = [0] * (lb + 1)
+    for i in range(1, la + 1):
+        cur = [0] * (lb + 1)
+        ai = a[i - 1]
+        for j in range(1, lb + 1):
+            if ai == b[j - 1]:
+                cur[j] = prev[j - 1] + 1
+            else:
+                cur[j] = prev[j] if prev[j] >= cur[j - 1] else cur[j - 1]
+        prev = cur
+    lcs = prev[lb]
+    return (la + lb - (la + lb - 2 * lcs)) / (la + lb)
+
+
+_DATA_DIR = None
+
+
+def stage_example_data():
+    """Gunzip example_dataset/*.csv.gz into a temp dir and return it (settings.py:18,22,36-37)."""
+    global _DATA_DIR
+    if _DATA_DIR is not None:
+        return _DATA_DIR
+    target = tempfile.mkdtemp(prefix='ds_ref_data_')
+    source = os.path.join(REFERENCE_ROOT, 'example_dataset')
+    for name in os.listdir(source):
+        if name.endswith('.csv.gz'):
+            with gzip.open(os.path.join(source, name), 'rb') as fin, \
+                    open(os.path.join(target, name[:-3]), 'wb') as fout:
+                shutil.copyfileobj(fin, fout)
+    _DATA_DIR = target
+    return target
+
+
+def import_reference():
+    """Returns the imported reference modules as a namespace (common, match_maker, feature_engineering,
+    predict, settings, constants)."""
+    if not reference_available():
+        raise RuntimeError('/root/reference is not present (GPU box?) - the reference cannot be imported here')
+    if 'Levenshtein' not in sys.modules:
+        lev = types.ModuleType('Levenshtein')
+        lev.ratio = _indel_ratio_py
+        sys.modules['Levenshtein'] = lev
+    if 'xgboost' not in sys.modules:
+        sys.modules['xgboost'] = types.ModuleType('xgboost')
+    os.environ['PROJECT_DATA_PATH'] = stage_example_data()
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    import doppelspeller.settings as settings
+    import doppelspeller.constants as constants
+    import doppelspeller.common as common
+    import doppelspeller.match_maker as match_maker
+    import doppelspeller.feature_engineering as feature_engineering
+    import doppelspeller.predict as predict
+    return types.SimpleNamespace(
+        settings=settings, constants=constants, common=common, match_maker=match_maker,
+        feature_engineering=feature_engineering, predict=predict)
