@@ -1,0 +1,1281 @@
+// ds_topn.cu - K1: IDF-weighted trigram Jaccard scan of the truth index fused with the reference's
+// top-n selection rule, plus the index build and the sharded local / merge / rescan phases.
+//
+// Reference semantics reproduced bit-for-bit (paths relative to /root/reference):
+//   score    doppelspeller/match_maker.py:16-50   fast_jaccard
+//            sc = f32 sequential sum, in ASCENDING column id order, of idf32 over the columns the
+//            query and the truth row share; s64 = f64(sc) / (f64(sums) + (mx - f64(sc)))
+//   select   doppelspeller/match_maker.py:53-71   fast_arg_top_k
+//            T = k-th largest f32(s64) over positive scores (0 when fewer than k),
+//            thr = f64(T) - f64(f32(1e-6)); result = the k HIGHEST row indexes with s64 >= thr,
+//            in descending row order.
+//   mx       doppelspeller/match_maker.py:197     python sum() over the ascending column ids
+//
+// Design (B200): the truth rows live in HBM as 16-byte chunks of eight ascending u16 column ids
+// (sentinel padded); a CTA owns a tile of up to 32 queries whose columns are scattered once into a
+// shared-memory direct map  column id -> slot -> (32-bit query mask, idf32)  and then streams truth
+// rows, one row per thread, with 32 register accumulators.  Adding the row's columns in ascending
+// order reproduces the reference's float32 accumulation order for every (query, row) pair at once;
+// the score matrix never exists.  Selection is a conservative float32 threshold test per pair
+// (no false negatives, see `filter_from_threshold`); survivors are re-scored in float64 exactly as
+// the reference does and merged into a per-query retained list that drives the threshold.
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <new>
+
+#include "ds_common.cuh"
+
+namespace ds {
+
+thread_local char g_last_error[512] = "";
+std::atomic<int64_t> g_kernel_launches{0};
+
+constexpr int TQ = 32;              // queries per tile (one bit each in the slot mask)
+constexpr int MAX_SLOTS = 2048;     // slot 0 = "column not in this tile"
+constexpr int CAND_CAP = 1024;      // per query candidate buffer (per scan launch)
+constexpr int DENSE_ROWS = 256;     // rows of the first (dense, threshold seeding) chunk
+constexpr int FIXED_ROWS = 1024;    // chunk rows of the bounded-memory fallback / rescan passes
+constexpr int QUERY_BATCH = 65536;  // queries per workspace batch
+constexpr int STATE_OVERFLOW = 1;
+
+struct Index {
+    int device = 0;
+    int64_t n_truth = 0;
+    int32_t n_vocab = 0;
+    int64_t row_offset = 0;
+    int64_t n_total = 0;
+    uint64_t n_chunks = 0;
+    uint4 *chunks = nullptr;        // [n_chunks] eight ascending u16 column ids, sentinel = n_vocab
+    uint32_t *chunk_ptr = nullptr;  // [n_truth + 1]
+    float *sums = nullptr;          // [n_truth] sums_matrix_truth
+    float *w32 = nullptr;           // [n_vocab + 1], w32[n_vocab] = 0 (sentinel)
+    double *w64 = nullptr;          // [n_vocab]
+};
+
+// ---------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------
+// s64 exactly as numba evaluates `scores / (sums + (mx - scores))` (match_maker.py:50): float64, this
+// association, one IEEE rounding per operation, no FMA contraction.
+__device__ __forceinline__ double exact_score(float sc, float sum_truth, double mx) {
+    double sc64 = (double)sc;
+    double den = __dadd_rn((double)sum_truth, __dsub_rn(mx, sc64));
+    return __ddiv_rn(sc64, den);
+}
+
+// Conservative float32 pre-filter for "s64 >= theta":  sc > fmaf(a, sums, b).
+// For theta > 0:  s64 >= theta  <=>  sc >= c (sums + mx), c = theta / (1 + theta).  a and b are rounded
+// DOWN with a 4e-6 relative margin, two orders of magnitude above the float32 rounding of the test
+// itself and the float64 rounding of s64, so a true qualifier can never be rejected.  theta <= 0 gives
+// a = b = 0, i.e. every positive score passes.
+__device__ __forceinline__ float2 filter_from_threshold(double theta, double mx) {
+    if (!(theta > 0.0)) return make_float2(0.0f, 0.0f);
+    double c = theta / (1.0 + theta);
+    float a = __double2float_rd(c * (1.0 - 4e-6));
+    float b = __double2float_rd((double)a * mx * (1.0 - 1e-6));
+    if (!(b >= 0.0f)) b = 0.0f;
+    return make_float2(a, b);
+}
+
+__device__ __forceinline__ double threshold_from_key(float kth_key) {
+    const float buffer = 1e-6f;  // settings.py:72 np.finfo(np.float32).resolution
+    return __dsub_rn((double)kth_key, (double)buffer);
+}
+
+// strict total order "better": higher score first, ties: higher row first
+__device__ __forceinline__ bool better(double sa, int64_t ra, double sb, int64_t rb) {
+    return sa > sb || (sa == sb && ra > rb);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// index build kernels
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_weights(const double *__restrict__ w64, float *__restrict__ w32, int n_vocab) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_vocab) w32[i] = (float)w64[i];  // numpy astype(float32): round to nearest even
+    if (i == n_vocab) w32[i] = 0.0f;
+}
+
+// one thread per row: chunk count and (optionally) sums_matrix_truth = sequential f32 sum in the
+// caller's column order (match_maker.py:172-174)
+__global__ void k_row_prepare(const int64_t *__restrict__ row_ptr, const uint16_t *__restrict__ cols,
+                              const float *__restrict__ w32, int n_vocab, int64_t n_rows, uint32_t *__restrict__ n_chunks,
+                              float *__restrict__ sums, int compute_sums) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    int64_t p0 = row_ptr[r], p1 = row_ptr[r + 1];
+    n_chunks[r] = (uint32_t)((p1 - p0 + 7) / 8);
+    if (compute_sums) {
+        float acc = 0.0f;
+        for (int64_t p = p0; p < p1; ++p) acc = __fadd_rn(acc, w32[min((int)cols[p], n_vocab)]);
+        sums[r] = acc;
+    }
+}
+
+// one warp per row: rank-sort the row's column ids ascending into its sentinel padded chunks
+__global__ void k_row_pack(const int64_t *__restrict__ row_ptr, const uint16_t *__restrict__ cols,
+                           const uint32_t *__restrict__ chunk_ptr, int64_t n_rows, uint16_t sentinel,
+                           uint16_t *__restrict__ out) {
+    int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+    int lane = threadIdx.x & 31;
+    if (r >= n_rows) return;
+    int64_t p0 = row_ptr[r];
+    int g = (int)(row_ptr[r + 1] - p0);
+    uint16_t *dst = out + (size_t)chunk_ptr[r] * 8;
+    int padded = (int)(chunk_ptr[r + 1] - chunk_ptr[r]) * 8;
+    for (int i = lane; i < padded; i += 32) {
+        if (i >= g) dst[i] = sentinel;
+    }
+    for (int i = lane; i < g; i += 32) {
+        uint16_t x = min(cols[p0 + i], sentinel);
+        int rank = 0;
+        for (int j = 0; j < g; ++j) {
+            uint16_t y = min(cols[p0 + j], sentinel);
+            rank += (y < x) || (y == x && j < i);
+        }
+        dst[rank] = x;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// query preparation: ascending column ids (match_maker.py:111-120) and mx (match_maker.py:197)
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_query_prepare(const int64_t *__restrict__ q_ptr, const uint16_t *__restrict__ q_cols,
+                                const double *__restrict__ w64, int n_vocab, const double *__restrict__ mx_in, int mx_mode,
+                                int64_t n_q, uint16_t *__restrict__ sorted, double *__restrict__ mx_out) {
+    int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+    int lane = threadIdx.x & 31;
+    if (q >= n_q) return;
+    int64_t p0 = q_ptr[q];
+    int g = (int)(q_ptr[q + 1] - p0);
+    for (int i = lane; i < g; i += 32) {
+        uint16_t x = min(q_cols[p0 + i], (uint16_t)n_vocab);  // out-of-range ids become the weightless sentinel
+        int rank = 0;
+        for (int j = 0; j < g; ++j) {
+            uint16_t y = min(q_cols[p0 + j], (uint16_t)n_vocab);
+            rank += (y < x) || (y == x && j < i);
+        }
+        sorted[p0 + rank] = x;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        if (mx_in != nullptr) {
+            mx_out[q] = mx_in[q];
+        } else {
+            // CPython's builtin sum() over python floats (Python/bltinmodule.c): the first item is added to
+            // int 0 exactly; the remaining ones go through Neumaier's compensated loop on >= 3.12.
+            double s = 0.0, c = 0.0;
+            for (int i = 0; i < g; ++i) {
+                int col = sorted[p0 + i];
+                double x = col < n_vocab ? w64[col] : 0.0;
+                if (i == 0) {
+                    s = x;
+                    continue;
+                }
+                double t = __dadd_rn(s, x);
+                if (mx_mode == DS_MX_PY312_COMPENSATED) {
+                    if (fabs(s) >= fabs(x)) c = __dadd_rn(c, __dadd_rn(__dsub_rn(s, t), x));
+                    else c = __dadd_rn(c, __dadd_rn(__dsub_rn(x, t), s));
+                }
+                s = t;
+            }
+            if (c != 0.0 && isfinite(c)) s = __dadd_rn(s, c);
+            mx_out[q] = s;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1 scan kernel
+// ---------------------------------------------------------------------------------------------------
+struct ScanParams {
+    const uint4 *chunks;
+    const uint32_t *chunk_ptr;
+    const float *sums;
+    const float *w32;
+    int n_vocab;
+    const uint16_t *q_sorted;   // call-level CSR, ascending per query
+    const int64_t *q_ptr;
+    const int32_t *batch_q;     // [n_batch] batch-local -> call-level query id
+    const int32_t *tile_q;      // [n_tiles * TQ] batch-local query ids, -1 = empty slot
+    const float2 *ab;           // [n_batch] filter constants
+    int r0, r1, rows_per_cta;
+    uint2 *cand;                // [n_batch * cap] (local row, f32 bits of sc)
+    int *cand_count;            // [n_batch]
+    int cap;
+    float *dense;               // non-null: write every sc to dense[b * dense_stride + (row - r0)]
+    int dense_stride;
+};
+
+__device__ __forceinline__ void accumulate_column(float (&sc)[TQ], uint32_t mask, float w) {
+#pragma unroll
+    for (int j = 0; j < TQ; ++j) {
+        if (mask & (1u << j)) sc[j] = __fadd_rn(sc[j], w);
+    }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 512 / THREADS) k_scan(ScanParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int slot_bytes = ((p.n_vocab + 1) * 2 + 15) & ~15;
+    uint16_t *slot16 = reinterpret_cast<uint16_t *>(smem);
+    uint2 *entries = reinterpret_cast<uint2 *>(smem + slot_bytes);
+    float2 *s_ab = reinterpret_cast<float2 *>(smem + slot_bytes + MAX_SLOTS * 8);
+    int *s_qid = reinterpret_cast<int *>(smem + slot_bytes + MAX_SLOTS * 8 + TQ * 8);
+    int *s_base = s_qid + TQ;
+
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.y;
+    const int cta_r0 = p.r0 + blockIdx.x * p.rows_per_cta;
+    const int cta_r1 = min(p.r1, cta_r0 + p.rows_per_cta);
+
+    // ---- build the tile table ----
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(smem);
+        const int n16 = (slot_bytes + MAX_SLOTS * 8) / 16;
+        for (int i = tid; i < n16; i += THREADS) z[i] = make_uint4(0, 0, 0, 0);
+        if (tid < TQ) {
+            int b = p.tile_q[tile * TQ + tid];
+            s_qid[tid] = b;
+            int g = 0;
+            float2 ab = make_float2(__int_as_float(0x7f800000), __int_as_float(0x7f800000));  // +inf: never passes
+            if (b >= 0) {
+                int q = p.batch_q[b];
+                g = (int)(p.q_ptr[q + 1] - p.q_ptr[q]);
+                ab = p.ab[b];
+            }
+            s_ab[tid] = ab;
+            int incl = g;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (tid >= d) incl += v;
+            }
+            s_base[tid] = incl - g;
+        }
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int j = warp; j < TQ; j += THREADS / 32) {
+        int b = s_qid[j];
+        if (b < 0) continue;
+        int q = p.batch_q[b];
+        int64_t q0 = p.q_ptr[q];
+        int g = (int)(p.q_ptr[q + 1] - q0);
+        for (int i = lane; i < g; i += 32) slot16[p.q_sorted[q0 + i]] = (uint16_t)(s_base[j] + i + 1);
+    }
+    __syncthreads();
+    for (int j = warp; j < TQ; j += THREADS / 32) {
+        int b = s_qid[j];
+        if (b < 0) continue;
+        int q = p.batch_q[b];
+        int64_t q0 = p.q_ptr[q];
+        int g = (int)(p.q_ptr[q + 1] - q0);
+        for (int i = lane; i < g; i += 32) {
+            uint16_t col = p.q_sorted[q0 + i];
+            int s = slot16[col];
+            atomicOr(&entries[s].x, 1u << j);
+            entries[s].y = __float_as_uint(p.w32[col]);
+        }
+    }
+    __syncthreads();
+
+    // ---- stream the truth rows: one row per thread, all TQ queries at once ----
+    for (int row = cta_r0 + tid; row < cta_r1; row += THREADS) {
+        float sc[TQ];
+#pragma unroll
+        for (int j = 0; j < TQ; ++j) sc[j] = 0.0f;
+        const uint32_t c0 = p.chunk_ptr[row], c1 = p.chunk_ptr[row + 1];
+        const float sum_t = p.sums[row];
+        for (uint32_t c = c0; c < c1; ++c) {
+            const uint4 ch = __ldg(p.chunks + c);
+            const uint32_t words[4] = {ch.x, ch.y, ch.z, ch.w};
+            uint2 ent[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                uint32_t col = (words[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+                ent[i] = entries[slot16[col]];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) accumulate_column(sc, ent[i].x, __uint_as_float(ent[i].y));
+        }
+        if (p.dense != nullptr) {
+#pragma unroll
+            for (int j = 0; j < TQ; ++j) {
+                int b = s_qid[j];
+                if (b >= 0) p.dense[(size_t)b * p.dense_stride + (row - p.r0)] = sc[j];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < TQ; ++j) {
+                float2 ab = s_ab[j];
+                if (sc[j] > fmaf(ab.x, sum_t, ab.y)) {
+                    int b = s_qid[j];
+                    int pos = atomicAdd(p.cand_count + b, 1);
+                    if (pos < p.cap) p.cand[(size_t)b * p.cap + pos] = make_uint2((uint32_t)row, __float_as_uint(sc[j]));
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// selection: merge this launch's candidates into the per-query retained list (best m by score) and
+// refresh the threshold / filter constants.  One warp per batch query.
+// ---------------------------------------------------------------------------------------------------
+struct SelectParams {
+    const int32_t *batch_q;
+    const double *q_mx;
+    const float *sums;
+    int n_batch;
+    int k, m;
+    const uint2 *cand;
+    int *cand_count;
+    int cap;
+    const float *dense;
+    int dense_stride, dense_rows, dense_r0;
+    double *ret_score;  // [n_batch * m] descending
+    int32_t *ret_row;   // [n_batch * m] local rows
+    int *ret_n;
+    double *theta;      // [n_batch] current exact threshold (<= 0: none yet)
+    float2 *ab;
+    int *state;
+    int *overflow_count;
+    int max_items;      // smem capacity per warp
+};
+
+__global__ void __launch_bounds__(128) k_select(SelectParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 4 + warp;
+    if (b >= p.n_batch) return;
+    double *s_score = reinterpret_cast<double *>(smem) + (size_t)warp * p.max_items;
+    int32_t *s_row = reinterpret_cast<int32_t *>(smem + (size_t)4 * p.max_items * 8) + (size_t)warp * p.max_items;
+    __shared__ double s_kth[4];
+
+    if (p.state[b] & STATE_OVERFLOW) return;
+    const double mx = p.q_mx[p.batch_q[b]];
+    const double theta = p.theta[b];
+    int n = 0;
+    if (p.dense != nullptr) {
+        for (int i0 = 0; i0 < p.dense_rows; i0 += 32) {
+            int i = i0 + lane;
+            float sc = (i < p.dense_rows) ? p.dense[(size_t)b * p.dense_stride + i] : 0.0f;
+            int row = p.dense_r0 + i;
+            double s = 0.0;
+            bool pass = sc > 0.0f;
+            if (pass) {
+                s = exact_score(sc, p.sums[row], mx);
+                pass = s > 0.0 && s >= theta;
+            }
+            unsigned ballot = __ballot_sync(0xffffffffu, pass);
+            if (pass) {
+                int pos = n + __popc(ballot & ((1u << lane) - 1));
+                s_score[pos] = s;
+                s_row[pos] = row;
+            }
+            n += __popc(ballot);
+        }
+    } else {
+        int cnt = p.cand_count[b];
+        if (cnt == 0) return;
+        if (cnt > p.cap) {
+            if (lane == 0) {
+                p.state[b] |= STATE_OVERFLOW;
+                p.ab[b] = make_float2(__int_as_float(0x7f800000), __int_as_float(0x7f800000));
+                p.cand_count[b] = 0;
+                atomicAdd(p.overflow_count, 1);
+            }
+            return;
+        }
+        for (int i0 = 0; i0 < cnt; i0 += 32) {
+            int i = i0 + lane;
+            bool pass = false;
+            double s = 0.0;
+            int row = 0;
+            if (i < cnt) {
+                uint2 c = p.cand[(size_t)b * p.cap + i];
+                row = (int)c.x;
+                s = exact_score(__uint_as_float(c.y), p.sums[row], mx);
+                pass = s > 0.0 && s >= theta;
+            }
+            unsigned ballot = __ballot_sync(0xffffffffu, pass);
+            if (pass) {
+                int pos = n + __popc(ballot & ((1u << lane) - 1));
+                s_score[pos] = s;
+                s_row[pos] = row;
+            }
+            n += __popc(ballot);
+        }
+    }
+    if (n == 0) {
+        if (lane == 0 && p.dense == nullptr) p.cand_count[b] = 0;
+        return;
+    }
+    const int n_old = p.ret_n[b];
+    for (int i = lane; i < n_old; i += 32) {
+        s_score[n + i] = p.ret_score[(size_t)b * p.m + i];
+        s_row[n + i] = p.ret_row[(size_t)b * p.m + i];
+    }
+    const int total = n + n_old;
+    __syncwarp();
+    for (int i = lane; i < total; i += 32) {
+        const double si = s_score[i];
+        const int ri = s_row[i];
+        int rank = 0;
+        for (int j = 0; j < total; ++j) rank += better(s_score[j], s_row[j], si, ri);
+        if (rank < p.m) {
+            p.ret_score[(size_t)b * p.m + rank] = si;
+            p.ret_row[(size_t)b * p.m + rank] = ri;
+        }
+        if (rank == p.k - 1) s_kth[warp] = si;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        p.ret_n[b] = min(total, p.m);
+        if (p.dense == nullptr) p.cand_count[b] = 0;
+        if (total >= p.k) {
+            double th = threshold_from_key(__double2float_rn(s_kth[warp]));
+            p.theta[b] = th;
+            p.ab[b] = filter_from_threshold(th, mx);
+        }
+    }
+}
+
+// copy the retained lists to the phase-1 output layout: [n_q, m] score desc / global row, -1 padded
+__global__ void k_export(const int32_t *__restrict__ batch_q, int n_batch, int m, const double *__restrict__ ret_score,
+                         const int32_t *__restrict__ ret_row, const int *__restrict__ ret_n, int64_t row_offset,
+                         double *__restrict__ out_score, int64_t *__restrict__ out_row) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n_batch * m) return;
+    int b = (int)(i / m), slot = (int)(i % m);
+    int64_t q = batch_q[b];
+    bool valid = slot < ret_n[b];
+    out_score[q * m + slot] = valid ? ret_score[i] : -1.0;
+    out_row[q * m + slot] = valid ? (int64_t)ret_row[i] + row_offset : -1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// merge (phase 2): one CTA per query over the gathered [n_shards, n_q, m] candidates
+// ---------------------------------------------------------------------------------------------------
+struct MergeParams {
+    int n_shards;
+    int64_t n_q;
+    int k, m;
+    int64_t n_total;
+    const double *all_score;
+    const int64_t *all_row;
+    const double *q_mx;  // nullable
+    int64_t *out_rows;
+    int32_t *out_count;
+    float *out_kth;
+    double *out_threshold;
+    int32_t *out_flags;
+    int *flagged_count;
+};
+
+__global__ void __launch_bounds__(128) k_merge(MergeParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int64_t q = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int cap = p.n_shards * p.m;
+    double *u_score = reinterpret_cast<double *>(smem);
+    int64_t *u_row = reinterpret_cast<int64_t *>(smem + (size_t)cap * 8);
+    __shared__ int s_n, s_incomplete, s_nqual;
+    __shared__ double s_kth;
+    if (tid == 0) {
+        s_n = 0;
+        s_incomplete = 0;
+        s_nqual = 0;
+        s_kth = 0.0;
+    }
+    __syncthreads();
+    for (int i = tid; i < cap; i += blockDim.x) {
+        int shard = i / p.m, slot = i % p.m;
+        size_t src = ((size_t)shard * p.n_q + q) * p.m + slot;
+        int64_t row = p.all_row[src];
+        if (row >= 0) {
+            int pos = atomicAdd(&s_n, 1);
+            u_score[pos] = p.all_score[src];
+            u_row[pos] = row;
+        }
+    }
+    __syncthreads();
+    const int n = s_n;
+    if (n >= p.k) {
+        for (int i = tid; i < n; i += blockDim.x) {
+            int rank = 0;
+            const double si = u_score[i];
+            const int64_t ri = u_row[i];
+            for (int j = 0; j < n; ++j) rank += better(u_score[j], u_row[j], si, ri);
+            if (rank == p.k - 1) s_kth = si;
+        }
+    }
+    __syncthreads();
+    const float kth_key = (n >= p.k) ? __double2float_rn(s_kth) : 0.0f;
+    const double thr = threshold_from_key(kth_key);
+    int64_t *rows = p.out_rows + q * p.k;
+    int flags = 0;
+    if (!(thr > 0.0)) {
+        // every row with a non-NaN score qualifies (scores are >= 0): the last k rows of the DB, unless the
+        // query has mx == 0, where rows with sums == 0 score 0/0 = NaN and must be skipped by the rescan.
+        flags = DS_FLAG_FEW_POSITIVE;
+        bool nan_risk = (p.q_mx != nullptr) && (p.q_mx[q] == 0.0);
+        if (nan_risk) flags |= DS_FLAG_RESCAN;
+        int64_t count = min((int64_t)p.k, p.n_total);
+        for (int i = tid; i < p.k; i += blockDim.x) rows[i] = (i < count) ? (p.n_total - 1 - i) : -1;
+        if (tid == 0) p.out_count[q] = (int32_t)count;
+    } else {
+        // a shard whose list is full may hold further qualifiers iff its lowest retained score qualifies
+        if (tid < p.n_shards) {
+            size_t last = ((size_t)tid * p.n_q + q) * p.m + (p.m - 1);
+            if (p.all_row[last] >= 0 && p.all_score[last] >= thr) s_incomplete = 1;
+        }
+        __syncthreads();
+        if (s_incomplete) {
+            flags = DS_FLAG_RESCAN;
+            for (int i = tid; i < p.k; i += blockDim.x) rows[i] = -1;
+            if (tid == 0) p.out_count[q] = 0;
+        } else {
+            for (int i = tid; i < p.k; i += blockDim.x) rows[i] = -1;
+            __syncthreads();
+            for (int i = tid; i < n; i += blockDim.x) {
+                if (!(u_score[i] >= thr)) continue;
+                atomicAdd(&s_nqual, 1);
+                int rank = 0;
+                const int64_t ri = u_row[i];
+                for (int j = 0; j < n; ++j) rank += (u_score[j] >= thr) && (u_row[j] > ri);
+                if (rank < p.k) rows[rank] = ri;
+            }
+            __syncthreads();
+            if (tid == 0) p.out_count[q] = min(s_nqual, p.k);
+        }
+    }
+    if (tid == 0) {
+        if (p.out_kth) p.out_kth[q] = kth_key;
+        if (p.out_threshold) p.out_threshold[q] = thr;
+        if (p.out_flags) p.out_flags[q] = flags;
+        if ((flags & DS_FLAG_RESCAN) && p.flagged_count) atomicAdd(p.flagged_count, 1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// rescan (phase 3): the k highest local rows with s64 >= thr, walking dense chunks from the top
+// ---------------------------------------------------------------------------------------------------
+struct CollectParams {
+    const int32_t *batch_q;
+    const double *q_mx;
+    const double *threshold;  // call-level
+    const float *sums;
+    int n_batch, k;
+    const float *dense;
+    int dense_stride, dense_rows, dense_r0;
+    int64_t row_offset;
+    int64_t *out_rows;   // call-level [n_q * k]
+    int32_t *out_count;  // call-level
+    int *unfinished;
+};
+
+__global__ void __launch_bounds__(128) k_collect(CollectParams p) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 4 + warp;
+    if (b >= p.n_batch) return;
+    const int64_t q = p.batch_q[b];
+    int count = p.out_count[q];
+    if (count >= p.k) return;
+    const double mx = p.q_mx[q], thr = p.threshold[q];
+    for (int i0 = p.dense_rows - 1; i0 >= 0 && count < p.k; i0 -= 32) {
+        int i = i0 - lane;  // lane order = descending row
+        bool pass = false;
+        if (i >= 0) {
+            float sc = p.dense[(size_t)b * p.dense_stride + i];
+            double s = exact_score(sc, p.sums[p.dense_r0 + i], mx);
+            pass = s >= thr;  // NaN compares false, like numpy's `array >= threshold`
+        }
+        unsigned ballot = __ballot_sync(0xffffffffu, pass);
+        if (pass) {
+            int pos = count + __popc(ballot & ((1u << lane) - 1));
+            if (pos < p.k) p.out_rows[q * p.k + pos] = (int64_t)(p.dense_r0 + i) + p.row_offset;
+        }
+        count += __popc(ballot);
+    }
+    if (lane == 0) {
+        p.out_count[q] = min(count, p.k);
+        if (count < p.k) atomicAdd(p.unfinished, 1);
+    }
+}
+
+__global__ void k_fill_i32(int32_t *p, int64_t n, int32_t v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+__global__ void k_rescan_reset(const int32_t *batch_q, int n_batch, int k, int64_t *out_rows, int32_t *out_count) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n_batch * k) return;
+    int b = (int)(i / k), slot = (int)(i % k);
+    int64_t q = batch_q[b];
+    out_rows[q * k + slot] = -1;
+    if (slot == 0) out_count[q] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+struct QuerySet {
+    int64_t n_q = 0;
+    std::vector<int64_t> h_ptr;
+    const int64_t *d_ptr = nullptr;
+    uint16_t *d_sorted = nullptr;
+    double *d_mx = nullptr;
+};
+
+static size_t scan_smem_bytes(int n_vocab) {
+    size_t slot_bytes = (((size_t)n_vocab + 1) * 2 + 15) & ~(size_t)15;
+    return slot_bytes + MAX_SLOTS * 8 + TQ * 8 + TQ * 4 * 2;
+}
+
+static int prepare_queries(Workspace &ws, const Index &ix, int64_t n_q, const int64_t *q_row_ptr,
+                           const uint16_t *q_col_ids, const double *q_mx, int32_t mx_mode, QuerySet *qs) {
+    cudaStream_t stream = ws.stream();
+    qs->n_q = n_q;
+    qs->h_ptr.resize((size_t)n_q + 1);
+    if (is_device_pointer(q_row_ptr)) {
+        DS_CUDA(cudaMemcpyAsync(qs->h_ptr.data(), q_row_ptr, (size_t)(n_q + 1) * 8, cudaMemcpyDeviceToHost, stream));
+        DS_CUDA(cudaStreamSynchronize(stream));
+    } else {
+        memcpy(qs->h_ptr.data(), q_row_ptr, (size_t)(n_q + 1) * 8);
+    }
+    const int64_t nnz = qs->h_ptr[n_q];
+    if (qs->h_ptr[0] != 0 || nnz < 0) return fail(DS_ERR_BAD_ARG, "q_row_ptr must start at 0 and be non-decreasing");
+    for (int64_t q = 0; q < n_q; ++q) {
+        int64_t g = qs->h_ptr[q + 1] - qs->h_ptr[q];
+        if (g < 0) return fail(DS_ERR_BAD_ARG, "q_row_ptr is decreasing at query %lld", (long long)q);
+        if (g > MAX_SLOTS - 1)
+            return fail(DS_ERR_UNSUPPORTED, "query %lld has %lld columns (max %d)", (long long)q, (long long)g, MAX_SLOTS - 1);
+    }
+    DS_CHECK(ws.stage_in(&qs->d_ptr, q_row_ptr, (size_t)n_q + 1));
+    const uint16_t *d_cols = nullptr;
+    DS_CHECK(ws.stage_in(&d_cols, q_col_ids, (size_t)nnz));
+    const double *d_mx_in = nullptr;
+    DS_CHECK(ws.stage_in(&d_mx_in, q_mx, (size_t)n_q));
+    DS_CHECK(ws.alloc(&qs->d_sorted, (size_t)nnz));
+    DS_CHECK(ws.alloc(&qs->d_mx, (size_t)n_q));
+    if (n_q > 0) {
+        int64_t threads = n_q * 32;
+        k_query_prepare<<<(unsigned)ceil_div(threads, 256), 256, 0, stream>>>(qs->d_ptr, d_cols, ix.w64, ix.n_vocab, d_mx_in, mx_mode, n_q,
+                                                                              qs->d_sorted, qs->d_mx);
+        DS_LAUNCHED("k_query_prepare");
+    }
+    return DS_OK;
+}
+
+// tiles: queries grouped by column count so that a tile's columns fit the slot table
+static void plan_tiles(const QuerySet &qs, const std::vector<int32_t> &batch, std::vector<int32_t> *tile_q) {
+    // class c holds queries with at most limit[c] columns, tiles of size[c] queries
+    const int limits[6] = {63, 127, 255, 511, 1023, MAX_SLOTS - 1};
+    const int sizes[6] = {32, 16, 8, 4, 2, 1};
+    std::vector<int32_t> classes[6];
+    for (int32_t b = 0; b < (int32_t)batch.size(); ++b) {
+        int64_t q = batch[b];
+        int64_t g = qs.h_ptr[q + 1] - qs.h_ptr[q];
+        int c = 0;
+        while (g > limits[c]) ++c;
+        classes[c].push_back(b);
+    }
+    tile_q->clear();
+    for (int c = 0; c < 6; ++c) {
+        const std::vector<int32_t> &members = classes[c];
+        for (size_t i = 0; i < members.size(); i += sizes[c]) {
+            size_t base = tile_q->size();
+            tile_q->resize(base + TQ, -1);
+            for (int j = 0; j < sizes[c] && i + j < members.size(); ++j) (*tile_q)[base + j] = members[i + j];
+        }
+    }
+}
+
+static int launch_scan(const Index &ix, cudaStream_t stream, ScanParams sp, int n_tiles) {
+    const size_t smem = scan_smem_bytes(ix.n_vocab);
+    const int64_t rows = sp.r1 - sp.r0;
+    if (rows <= 0 || n_tiles <= 0) return DS_OK;
+    const bool big = smem > 110 * 1024;
+    const int threads = big ? 512 : 256;
+    // enough CTAs to fill 148 SMs a few times, but at least 4 rows per thread to amortise the table build
+    int64_t rows_per_cta = std::max<int64_t>(threads * 4, ceil_div(rows, std::max<int64_t>(1, ceil_div(148 * 32, n_tiles))));
+    rows_per_cta = ceil_div(rows_per_cta, threads) * threads;
+    sp.rows_per_cta = (int)std::min<int64_t>(rows_per_cta, 1 << 30);
+    int64_t row_ctas = ceil_div(rows, sp.rows_per_cta);
+    for (int t0 = 0; t0 < n_tiles; t0 += 65535) {
+        int nt = std::min(65535, n_tiles - t0);
+        ScanParams part = sp;
+        part.tile_q = sp.tile_q + (size_t)t0 * TQ;
+        dim3 grid((unsigned)row_ctas, (unsigned)nt);
+        if (big) {
+            static bool attr_done = false;
+            if (!attr_done) {
+                DS_CUDA(cudaFuncSetAttribute(k_scan<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                attr_done = true;
+            }
+            k_scan<512><<<grid, 512, smem, stream>>>(part);
+        } else {
+            static bool attr_done = false;
+            if (!attr_done) {
+                DS_CUDA(cudaFuncSetAttribute(k_scan<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+                attr_done = true;
+            }
+            k_scan<256><<<grid, 256, smem, stream>>>(part);
+        }
+        DS_LAUNCHED("k_scan");
+    }
+    return DS_OK;
+}
+
+static int launch_select(cudaStream_t stream, SelectParams sp) {
+    if (sp.n_batch <= 0) return DS_OK;
+    int items = std::max(sp.cap, sp.dense_rows) + sp.m;
+    sp.max_items = items;
+    size_t smem = (size_t)4 * items * 12;
+    static size_t attr_bytes = 0;
+    if (smem > 48 * 1024 && smem > attr_bytes) {
+        DS_CUDA(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_bytes = smem;
+    }
+    k_select<<<(unsigned)ceil_div(sp.n_batch, 4), 128, smem, stream>>>(sp);
+    DS_LAUNCHED("k_select");
+    return DS_OK;
+}
+
+// Runs the scan + select pipeline for one batch of queries (ids into the call's query set) and
+// exports its retained lists.  `fixed` = bounded-memory mode: dense chunks of FIXED_ROWS rows only.
+static int run_local_batch(Workspace &call_ws, const Index &ix, const QuerySet &qs, const std::vector<int32_t> &batch,
+                           int k, int m, bool fixed, double *d_out_score, int64_t *d_out_row,
+                           std::vector<int32_t> *overflowed) {
+    cudaStream_t stream = call_ws.stream();
+    const int n_batch = (int)batch.size();
+    if (n_batch == 0) return DS_OK;
+    Workspace ws(stream);
+    std::vector<int32_t> tile_q;
+    plan_tiles(qs, batch, &tile_q);
+    const int n_tiles = (int)(tile_q.size() / TQ);
+
+    int32_t *d_batch = nullptr, *d_tile = nullptr, *d_ret_row = nullptr;
+    int *d_cand_count = nullptr, *d_ret_n = nullptr, *d_state = nullptr, *d_overflow = nullptr;
+    float2 *d_ab = nullptr;
+    uint2 *d_cand = nullptr;
+    double *d_ret_score = nullptr, *d_theta = nullptr;
+    float *d_dense = nullptr;
+    const int dense_rows = fixed ? FIXED_ROWS : std::max(DENSE_ROWS, ((2 * k + 255) / 256) * 256);
+    DS_CHECK(ws.alloc(&d_batch, n_batch));
+    DS_CHECK(ws.alloc(&d_tile, tile_q.size()));
+    DS_CHECK(ws.alloc(&d_ret_row, (size_t)n_batch * m));
+    DS_CHECK(ws.alloc(&d_ret_score, (size_t)n_batch * m));
+    DS_CHECK(ws.alloc(&d_cand_count, n_batch));
+    DS_CHECK(ws.alloc(&d_ret_n, n_batch));
+    DS_CHECK(ws.alloc(&d_state, n_batch));
+    DS_CHECK(ws.alloc(&d_overflow, 1));
+    DS_CHECK(ws.alloc(&d_ab, n_batch));
+    DS_CHECK(ws.alloc(&d_theta, n_batch));
+    DS_CHECK(ws.alloc(&d_dense, (size_t)n_batch * dense_rows));
+    if (!fixed) DS_CHECK(ws.alloc(&d_cand, (size_t)n_batch * CAND_CAP));
+    DS_CUDA(cudaMemcpyAsync(d_batch, batch.data(), (size_t)n_batch * 4, cudaMemcpyHostToDevice, stream));
+    DS_CUDA(cudaMemcpyAsync(d_tile, tile_q.data(), tile_q.size() * 4, cudaMemcpyHostToDevice, stream));
+    DS_CUDA(cudaMemsetAsync(d_cand_count, 0, (size_t)n_batch * 4, stream));
+    DS_CUDA(cudaMemsetAsync(d_ret_n, 0, (size_t)n_batch * 4, stream));
+    DS_CUDA(cudaMemsetAsync(d_state, 0, (size_t)n_batch * 4, stream));
+    DS_CUDA(cudaMemsetAsync(d_overflow, 0, 4, stream));
+    DS_CUDA(cudaMemsetAsync(d_ab, 0, (size_t)n_batch * 8, stream));
+    DS_CUDA(cudaMemsetAsync(d_theta, 0, (size_t)n_batch * 8, stream));
+
+    ScanParams sp{};
+    sp.chunks = ix.chunks;
+    sp.chunk_ptr = ix.chunk_ptr;
+    sp.sums = ix.sums;
+    sp.w32 = ix.w32;
+    sp.n_vocab = ix.n_vocab;
+    sp.q_sorted = qs.d_sorted;
+    sp.q_ptr = qs.d_ptr;
+    sp.batch_q = d_batch;
+    sp.tile_q = d_tile;
+    sp.ab = d_ab;
+    sp.cand = d_cand;
+    sp.cand_count = d_cand_count;
+    sp.cap = CAND_CAP;
+    sp.dense_stride = dense_rows;
+
+    SelectParams sel{};
+    sel.batch_q = d_batch;
+    sel.q_mx = qs.d_mx;
+    sel.sums = ix.sums;
+    sel.n_batch = n_batch;
+    sel.k = k;
+    sel.m = m;
+    sel.cand = d_cand;
+    sel.cand_count = d_cand_count;
+    sel.cap = fixed ? 0 : CAND_CAP;
+    sel.dense_stride = dense_rows;
+    sel.ret_score = d_ret_score;
+    sel.ret_row = d_ret_row;
+    sel.ret_n = d_ret_n;
+    sel.theta = d_theta;
+    sel.ab = d_ab;
+    sel.state = d_state;
+    sel.overflow_count = d_overflow;
+
+    const int64_t n = ix.n_truth;
+    int64_t r0 = 0;
+    bool first = true;
+    while (r0 < n) {
+        const bool dense = fixed || first;
+        int64_t r1 = dense ? std::min<int64_t>(n, r0 + dense_rows) : std::min<int64_t>(n, std::max<int64_t>(2 * r0, r0 + dense_rows));
+        sp.r0 = (int)r0;
+        sp.r1 = (int)r1;
+        sp.dense = dense ? d_dense : nullptr;
+        DS_CHECK(launch_scan(ix, stream, sp, n_tiles));
+        sel.dense = dense ? d_dense : nullptr;
+        sel.dense_rows = dense ? (int)(r1 - r0) : 0;
+        sel.dense_r0 = (int)r0;
+        DS_CHECK(launch_select(stream, sel));
+        r0 = r1;
+        first = false;
+    }
+    k_export<<<(unsigned)ceil_div((int64_t)n_batch * m, 256), 256, 0, stream>>>(d_batch, n_batch, m, d_ret_score, d_ret_row,
+                                                                                d_ret_n, ix.row_offset, d_out_score, d_out_row);
+    DS_LAUNCHED("k_export");
+    if (!fixed && overflowed != nullptr) {
+        int h_overflow = 0;
+        DS_CUDA(cudaMemcpyAsync(&h_overflow, d_overflow, 4, cudaMemcpyDeviceToHost, stream));
+        DS_CUDA(cudaStreamSynchronize(stream));
+        if (h_overflow > 0) {
+            std::vector<int> h_state(n_batch);
+            DS_CUDA(cudaMemcpyAsync(h_state.data(), d_state, (size_t)n_batch * 4, cudaMemcpyDeviceToHost, stream));
+            DS_CUDA(cudaStreamSynchronize(stream));
+            for (int b = 0; b < n_batch; ++b)
+                if (h_state[b] & STATE_OVERFLOW) overflowed->push_back(batch[b]);
+        }
+    }
+    return DS_OK;
+}
+
+static int local_topn(Workspace &ws, const Index &ix, const QuerySet &qs, int k, int m, double *d_out_score,
+                      int64_t *d_out_row) {
+    std::vector<int32_t> overflowed;
+    for (int64_t q0 = 0; q0 < qs.n_q; q0 += QUERY_BATCH) {
+        int64_t q1 = std::min<int64_t>(qs.n_q, q0 + QUERY_BATCH);
+        std::vector<int32_t> batch((size_t)(q1 - q0));
+        for (int64_t q = q0; q < q1; ++q) batch[(size_t)(q - q0)] = (int32_t)q;
+        DS_CHECK(run_local_batch(ws, ix, qs, batch, k, m, false, d_out_score, d_out_row, &overflowed));
+    }
+    // queries whose candidate buffer overflowed (adversarial row order / massive ties) are redone in the
+    // bounded-memory mode, which cannot overflow
+    for (size_t i = 0; i < overflowed.size(); i += QUERY_BATCH / 8) {
+        size_t j = std::min(overflowed.size(), i + QUERY_BATCH / 8);
+        std::vector<int32_t> batch(overflowed.begin() + i, overflowed.begin() + j);
+        DS_CHECK(run_local_batch(ws, ix, qs, batch, k, m, true, d_out_score, d_out_row, nullptr));
+    }
+    return DS_OK;
+}
+
+static int merge_topn(cudaStream_t stream, int n_shards, int64_t n_q, int k, int m, int64_t n_total, const double *d_score,
+                      const int64_t *d_row, const double *d_mx, int64_t *d_out_rows, int32_t *d_out_count, float *d_out_kth,
+                      double *d_out_threshold, int32_t *d_out_flags, int *d_flagged_count) {
+    if (n_q <= 0) return DS_OK;
+    MergeParams mp{};
+    mp.n_shards = n_shards;
+    mp.n_q = n_q;
+    mp.k = k;
+    mp.m = m;
+    mp.n_total = n_total;
+    mp.all_score = d_score;
+    mp.all_row = d_row;
+    mp.q_mx = d_mx;
+    mp.out_rows = d_out_rows;
+    mp.out_count = d_out_count;
+    mp.out_kth = d_out_kth;
+    mp.out_threshold = d_out_threshold;
+    mp.out_flags = d_out_flags;
+    mp.flagged_count = d_flagged_count;
+    size_t smem = (size_t)n_shards * m * 16;
+    static size_t attr_bytes = 0;
+    if (smem > 48 * 1024 && smem > attr_bytes) {
+        if (smem > 227 * 1024) return fail(DS_ERR_UNSUPPORTED, "n_shards * retained (%d * %d) too large for the merge kernel", n_shards, m);
+        DS_CUDA(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_bytes = smem;
+    }
+    for (int64_t q0 = 0; q0 < n_q; q0 += 1 << 30) {  // grid.x limit is 2^31-1; kept for symmetry
+        k_merge<<<(unsigned)std::min<int64_t>(n_q - q0, 1 << 30), 128, smem, stream>>>(mp);
+        DS_LAUNCHED("k_merge");
+    }
+    return DS_OK;
+}
+
+// exact re-scan of the local shard for `flagged` queries with known thresholds (> 0 or the NaN edge)
+static int rescan_topn(Workspace &call_ws, const Index &ix, const QuerySet &qs, const double *d_threshold,
+                       const std::vector<int32_t> &flagged, int k, int64_t *d_out_rows, int32_t *d_out_count) {
+    cudaStream_t stream = call_ws.stream();
+    for (size_t i0 = 0; i0 < flagged.size(); i0 += QUERY_BATCH / 8) {
+        size_t i1 = std::min(flagged.size(), i0 + QUERY_BATCH / 8);
+        std::vector<int32_t> batch(flagged.begin() + i0, flagged.begin() + i1);
+        const int n_batch = (int)batch.size();
+        Workspace ws(stream);
+        std::vector<int32_t> tile_q;
+        plan_tiles(qs, batch, &tile_q);
+        const int n_tiles = (int)(tile_q.size() / TQ);
+        int32_t *d_batch = nullptr, *d_tile = nullptr;
+        float *d_dense = nullptr;
+        int *d_unfinished = nullptr;
+        float2 *d_ab = nullptr;
+        DS_CHECK(ws.alloc(&d_batch, n_batch));
+        DS_CHECK(ws.alloc(&d_tile, tile_q.size()));
+        DS_CHECK(ws.alloc(&d_dense, (size_t)n_batch * FIXED_ROWS));
+        DS_CHECK(ws.alloc(&d_unfinished, 1));
+        DS_CHECK(ws.alloc(&d_ab, n_batch));
+        DS_CUDA(cudaMemcpyAsync(d_batch, batch.data(), (size_t)n_batch * 4, cudaMemcpyHostToDevice, stream));
+        DS_CUDA(cudaMemcpyAsync(d_tile, tile_q.data(), tile_q.size() * 4, cudaMemcpyHostToDevice, stream));
+        DS_CUDA(cudaMemsetAsync(d_ab, 0, (size_t)n_batch * 8, stream));
+        k_rescan_reset<<<(unsigned)ceil_div((int64_t)n_batch * k, 256), 256, 0, stream>>>(d_batch, n_batch, k, d_out_rows, d_out_count);
+        DS_LAUNCHED("k_rescan_reset");
+
+        ScanParams sp{};
+        sp.chunks = ix.chunks;
+        sp.chunk_ptr = ix.chunk_ptr;
+        sp.sums = ix.sums;
+        sp.w32 = ix.w32;
+        sp.n_vocab = ix.n_vocab;
+        sp.q_sorted = qs.d_sorted;
+        sp.q_ptr = qs.d_ptr;
+        sp.batch_q = d_batch;
+        sp.tile_q = d_tile;
+        sp.ab = d_ab;
+        sp.dense = d_dense;
+        sp.dense_stride = FIXED_ROWS;
+        CollectParams cp{};
+        cp.batch_q = d_batch;
+        cp.q_mx = qs.d_mx;
+        cp.threshold = d_threshold;
+        cp.sums = ix.sums;
+        cp.n_batch = n_batch;
+        cp.k = k;
+        cp.dense = d_dense;
+        cp.dense_stride = FIXED_ROWS;
+        cp.row_offset = ix.row_offset;
+        cp.out_rows = d_out_rows;
+        cp.out_count = d_out_count;
+        cp.unfinished = d_unfinished;
+
+        int64_t r1 = ix.n_truth;
+        int iteration = 0;
+        while (r1 > 0) {
+            int64_t r0 = std::max<int64_t>(0, r1 - FIXED_ROWS);
+            sp.r0 = (int)r0;
+            sp.r1 = (int)r1;
+            DS_CHECK(launch_scan(ix, stream, sp, n_tiles));
+            DS_CUDA(cudaMemsetAsync(d_unfinished, 0, 4, stream));
+            cp.dense_rows = (int)(r1 - r0);
+            cp.dense_r0 = (int)r0;
+            k_collect<<<(unsigned)ceil_div(n_batch, 4), 128, 0, stream>>>(cp);
+            DS_LAUNCHED("k_collect");
+            r1 = r0;
+            if ((++iteration % 4) == 0 && r1 > 0) {
+                int h_unfinished = 0;
+                DS_CUDA(cudaMemcpyAsync(&h_unfinished, d_unfinished, 4, cudaMemcpyDeviceToHost, stream));
+                DS_CUDA(cudaStreamSynchronize(stream));
+                if (h_unfinished == 0) break;
+            }
+        }
+    }
+    return DS_OK;
+}
+
+static int check_topn_args(const Index *ix, int64_t n_q, const int64_t *q_row_ptr, const uint16_t *q_col_ids, int32_t k) {
+    if (ix == nullptr) return fail(DS_ERR_BAD_ARG, "index is NULL");
+    if (n_q < 0) return fail(DS_ERR_BAD_ARG, "n_q < 0");
+    if (n_q > 0 && q_row_ptr == nullptr) return fail(DS_ERR_BAD_ARG, "q_row_ptr is NULL");
+    if (k < 1 || k > DS_MAX_TOP_N) return fail(DS_ERR_UNSUPPORTED, "top_n %d outside 1..%d", k, DS_MAX_TOP_N);
+    if (n_q > INT32_MAX) return fail(DS_ERR_UNSUPPORTED, "n_q exceeds 2^31-1");
+    (void)q_col_ids;
+    return DS_OK;
+}
+
+}  // namespace ds
+
+using namespace ds;
+
+struct ds_index {
+    Index ix;
+};
+
+extern "C" {
+
+int ds_version(void) { return DS_VERSION; }
+const char *ds_last_error(void) { return g_last_error; }
+int64_t ds_kernel_launches(void) { return g_kernel_launches.load(); }
+
+int32_t ds_topn_retained(int32_t k) {
+    int extra = std::max(32, k / 4);
+    return ((k + extra + 31) / 32) * 32;
+}
+
+int ds_index_create(ds_index **out, int device, int64_t n_truth, int32_t n_vocab, const int64_t *t_row_ptr,
+                    const uint16_t *t_col_ids, const double *idf64_by_col, const float *sums_truth_f32,
+                    int64_t global_row_offset, int64_t n_truth_total, void *stream_) {
+    if (out == nullptr) return fail(DS_ERR_BAD_ARG, "out is NULL");
+    *out = nullptr;
+    if (n_truth < 0 || n_truth >= (int64_t)1 << 31) return fail(DS_ERR_UNSUPPORTED, "n_truth %lld outside 0..2^31-1", (long long)n_truth);
+    if (n_vocab < 1 || n_vocab > 65535) return fail(DS_ERR_UNSUPPORTED, "n_vocab %d outside 1..65535 (u16 column ids)", n_vocab);
+    if (t_row_ptr == nullptr || idf64_by_col == nullptr) return fail(DS_ERR_BAD_ARG, "t_row_ptr / idf64_by_col is NULL");
+    if (scan_smem_bytes(n_vocab) > 227 * 1024) return fail(DS_ERR_UNSUPPORTED, "n_vocab %d needs more than 227 KB of shared memory", n_vocab);
+    int n_devices = 0;
+    if (cudaGetDeviceCount(&n_devices) != cudaSuccess || n_devices == 0) {
+        cudaGetLastError();
+        return fail(DS_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= n_devices) return fail(DS_ERR_BAD_ARG, "device %d out of range (%d devices)", device, n_devices);
+    DeviceGuard guard(device);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+
+    int64_t nnz = 0;
+    if (is_device_pointer(t_row_ptr)) {
+        DS_CUDA(cudaMemcpyAsync(&nnz, t_row_ptr + n_truth, 8, cudaMemcpyDeviceToHost, stream));
+        DS_CUDA(cudaStreamSynchronize(stream));
+    } else {
+        nnz = t_row_ptr[n_truth];
+    }
+    if (nnz < 0) return fail(DS_ERR_BAD_ARG, "t_row_ptr[n_truth] < 0");
+    if (nnz > 0 && t_col_ids == nullptr) return fail(DS_ERR_BAD_ARG, "t_col_ids is NULL");
+
+    ds_index *handle = new (std::nothrow) ds_index();
+    if (handle == nullptr) return fail(DS_ERR_NO_MEMORY, "out of host memory");
+    Index &ix = handle->ix;
+    ix.device = device;
+    ix.n_truth = n_truth;
+    ix.n_vocab = n_vocab;
+    ix.row_offset = global_row_offset;
+    ix.n_total = n_truth_total > 0 ? n_truth_total : n_truth;
+    int status = [&]() -> int {
+        Workspace ws(stream);
+        const int64_t *d_ptr = nullptr;
+        const uint16_t *d_cols = nullptr;
+        const double *d_w64_in = nullptr;
+        const float *d_sums_in = nullptr;
+        DS_CHECK(ws.stage_in(&d_ptr, t_row_ptr, (size_t)n_truth + 1));
+        DS_CHECK(ws.stage_in(&d_cols, t_col_ids, (size_t)nnz));
+        DS_CHECK(ws.stage_in(&d_w64_in, idf64_by_col, (size_t)n_vocab));
+        DS_CHECK(ws.stage_in(&d_sums_in, sums_truth_f32, (size_t)n_truth));
+        DS_CUDA(cudaMalloc(&ix.w64, (size_t)n_vocab * 8));
+        DS_CUDA(cudaMalloc(&ix.w32, ((size_t)n_vocab + 1) * 4));
+        DS_CUDA(cudaMalloc(&ix.sums, (size_t)std::max<int64_t>(1, n_truth) * 4));
+        DS_CUDA(cudaMalloc(&ix.chunk_ptr, ((size_t)n_truth + 1) * 4));
+        DS_CUDA(cudaMemcpyAsync(ix.w64, d_w64_in, (size_t)n_vocab * 8, cudaMemcpyDeviceToDevice, stream));
+        k_weights<<<(unsigned)ceil_div(n_vocab + 1, 256), 256, 0, stream>>>(ix.w64, ix.w32, n_vocab);
+        DS_LAUNCHED("k_weights");
+        uint32_t *d_counts = nullptr;
+        DS_CHECK(ws.alloc(&d_counts, (size_t)n_truth + 1));
+        DS_CUDA(cudaMemsetAsync(d_counts, 0, ((size_t)n_truth + 1) * 4, stream));
+        if (n_truth > 0) {
+            if (d_sums_in != nullptr)
+                DS_CUDA(cudaMemcpyAsync(ix.sums, d_sums_in, (size_t)n_truth * 4, cudaMemcpyDeviceToDevice, stream));
+            k_row_prepare<<<(unsigned)ceil_div(n_truth, 256), 256, 0, stream>>>(d_ptr, d_cols, ix.w32, n_vocab, n_truth, d_counts, ix.sums,
+                                                                               d_sums_in == nullptr ? 1 : 0);
+            DS_LAUNCHED("k_row_prepare");
+        }
+        size_t temp_bytes = 0;
+        DS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, d_counts, ix.chunk_ptr, (int)(n_truth + 1), stream));
+        unsigned char *d_temp = nullptr;
+        DS_CHECK(ws.alloc(&d_temp, temp_bytes));
+        DS_CUDA(cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_counts, ix.chunk_ptr, (int)(n_truth + 1), stream));
+        g_kernel_launches.fetch_add(1);
+        uint32_t total_chunks = 0;
+        DS_CUDA(cudaMemcpyAsync(&total_chunks, ix.chunk_ptr + n_truth, 4, cudaMemcpyDeviceToHost, stream));
+        DS_CUDA(cudaStreamSynchronize(stream));
+        if (ceil_div(nnz, 8) + n_truth >= ((int64_t)1 << 32)) return fail(DS_ERR_UNSUPPORTED, "index too large for 32-bit chunk offsets");
+        ix.n_chunks = total_chunks;
+        DS_CUDA(cudaMalloc(&ix.chunks, std::max<size_t>(1, (size_t)total_chunks) * 16));
+        if (n_truth > 0) {
+            k_row_pack<<<(unsigned)ceil_div(n_truth * 32, 256), 256, 0, stream>>>(d_ptr, d_cols, ix.chunk_ptr, n_truth, (uint16_t)n_vocab,
+                                                                                 reinterpret_cast<uint16_t *>(ix.chunks));
+            DS_LAUNCHED("k_row_pack");
+        }
+        DS_CUDA(cudaStreamSynchronize(stream));
+        return DS_OK;
+    }();
+    if (status != DS_OK) {
+        ds_index_destroy(handle);
+        return status;
+    }
+    *out = handle;
+    return DS_OK;
+}
+
+int ds_index_destroy(ds_index *index) {
+    if (index == nullptr) return DS_OK;
+    DeviceGuard guard(index->ix.device);
+    cudaFree(index->ix.chunks);
+    cudaFree(index->ix.chunk_ptr);
+    cudaFree(index->ix.sums);
+    cudaFree(index->ix.w32);
+    cudaFree(index->ix.w64);
+    delete index;
+    return DS_OK;
+}
+
+int ds_index_get_sums(const ds_index *index, float *out, void *stream_) {
+    if (index == nullptr || out == nullptr) return fail(DS_ERR_BAD_ARG, "index / out is NULL");
+    DeviceGuard guard(index->ix.device);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DS_CUDA(cudaMemcpyAsync(out, index->ix.sums, (size_t)index->ix.n_truth * 4, cudaMemcpyDefault, stream));
+    if (!is_device_pointer(out)) DS_CUDA(cudaStreamSynchronize(stream));
+    return DS_OK;
+}
+
+int ds_topn_local(ds_index *index, int64_t n_q, const int64_t *q_row_ptr, const uint16_t *q_col_ids, const double *q_mx,
+                  int32_t mx_mode, int32_t k, double *out_score, int64_t *out_row, double *out_mx, void *stream_) {
+    DS_CHECK(check_topn_args(index ? &index->ix : nullptr, n_q, q_row_ptr, q_col_ids, k));
+    if (out_score == nullptr || out_row == nullptr) return fail(DS_ERR_BAD_ARG, "out_score / out_row is NULL");
+    const Index &ix = index->ix;
+    DeviceGuard guard(ix.device);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (n_q == 0) return DS_OK;
+    Workspace ws(stream);
+    QuerySet qs;
+    DS_CHECK(prepare_queries(ws, ix, n_q, q_row_ptr, q_col_ids, q_mx, mx_mode, &qs));
+    const int m = ds_topn_retained(k);
+    double *d_score = nullptr, *d_mx_out = nullptr;
+    int64_t *d_row = nullptr;
+    DS_CHECK(ws.stage_out(&d_score, out_score, (size_t)n_q * m));
+    DS_CHECK(ws.stage_out(&d_row, out_row, (size_t)n_q * m));
+    DS_CHECK(ws.stage_out(&d_mx_out, out_mx, (size_t)n_q));
+    DS_CHECK(local_topn(ws, ix, qs, k, m, d_score, d_row));
+    if (d_mx_out != nullptr) DS_CUDA(cudaMemcpyAsync(d_mx_out, qs.d_mx, (size_t)n_q * 8, cudaMemcpyDeviceToDevice, stream));
+    return ws.finish_outputs();
+}
+
+int ds_topn_merge(int32_t n_shards, int64_t n_q, int32_t k, int64_t n_truth_total, const double *all_score,
+                  const int64_t *all_row, const double *q_mx, int64_t *out_rows, int32_t *out_count, float *out_kth_f32,
+                  double *out_threshold, int32_t *out_flags, int device, void *stream_) {
+    if (n_shards < 1 || n_shards > 128) return fail(DS_ERR_BAD_ARG, "n_shards %d outside 1..128", n_shards);
+    if (n_q < 0 || k < 1 || k > DS_MAX_TOP_N) return fail(DS_ERR_BAD_ARG, "bad n_q / k");
+    if (n_q == 0) return DS_OK;
+    if (all_score == nullptr || all_row == nullptr || out_rows == nullptr || out_count == nullptr)
+        return fail(DS_ERR_BAD_ARG, "NULL argument");
+    DeviceGuard guard(device);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    Workspace ws(stream);
+    const int m = ds_topn_retained(k);
+    const double *d_score = nullptr, *d_mx = nullptr;
+    const int64_t *d_row = nullptr;
+    DS_CHECK(ws.stage_in(&d_score, all_score, (size_t)n_shards * n_q * m));
+    DS_CHECK(ws.stage_in(&d_row, all_row, (size_t)n_shards * n_q * m));
+    DS_CHECK(ws.stage_in(&d_mx, q_mx, (size_t)n_q));
+    int64_t *d_rows = nullptr;
+    int32_t *d_count = nullptr, *d_flags = nullptr;
+    float *d_kth = nullptr;
+    double *d_thr = nullptr;
+    DS_CHECK(ws.stage_out(&d_rows, out_rows, (size_t)n_q * k));
+    DS_CHECK(ws.stage_out(&d_count, out_count, (size_t)n_q));
+    DS_CHECK(ws.stage_out(&d_kth, out_kth_f32, (size_t)n_q));
+    DS_CHECK(ws.stage_out(&d_thr, out_threshold, (size_t)n_q));
+    DS_CHECK(ws.stage_out(&d_flags, out_flags, (size_t)n_q));
+    DS_CHECK(merge_topn(stream, n_shards, n_q, k, m, n_truth_total, d_score, d_row, d_mx, d_rows, d_count, d_kth, d_thr, d_flags, nullptr));
+    return ws.finish_outputs();
+}
+
+static int collect_flagged(cudaStream_t stream, const int32_t *d_flags, int64_t n_q, std::vector<int32_t> *flagged) {
+    std::vector<int32_t> h_flags((size_t)n_q);
+    DS_CUDA(cudaMemcpyAsync(h_flags.data(), d_flags, (size_t)n_q * 4, cudaMemcpyDeviceToHost, stream));
+    DS_CUDA(cudaStreamSynchronize(stream));
+    for (int64_t q = 0; q < n_q; ++q)
+        if (h_flags[(size_t)q] & DS_FLAG_RESCAN) flagged->push_back((int32_t)q);
+    return DS_OK;
+}
+
+int ds_topn_rescan(ds_index *index, int64_t n_q, const int64_t *q_row_ptr, const uint16_t *q_col_ids, const double *q_mx,
+                   const double *threshold, const int32_t *flags, int32_t k, int64_t *out_rows, int32_t *out_count,
+                   void *stream_) {
+    DS_CHECK(check_topn_args(index ? &index->ix : nullptr, n_q, q_row_ptr, q_col_ids, k));
+    if (threshold == nullptr || flags == nullptr || out_rows == nullptr || out_count == nullptr)
+        return fail(DS_ERR_BAD_ARG, "NULL argument");
+    const Index &ix = index->ix;
+    DeviceGuard guard(ix.device);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (n_q == 0) return DS_OK;
+    Workspace ws(stream);
+    const int32_t *d_flags = nullptr;
+    DS_CHECK(ws.stage_in(&d_flags, flags, (size_t)n_q));
+    std::vector<int32_t> flagged;
+    if (is_device_pointer(flags)) {
+        DS_CHECK(collect_flagged(stream, d_flags, n_q, &flagged));
+    } else {
+        for (int64_t q = 0; q < n_q; ++q)
+            if (flags[q] & DS_FLAG_RESCAN) flagged.push_back((int32_t)q);
+    }
+    if (flagged.empty()) return DS_OK;
+    if (q_mx == nullptr) return fail(DS_ERR_BAD_ARG, "ds_topn_rescan needs the q_mx returned by ds_topn_local");
+    QuerySet qs;
+    DS_CHECK(prepare_queries(ws, ix, n_q, q_row_ptr, q_col_ids, q_mx, 0, &qs));
+    const double *d_thr = nullptr;
+    DS_CHECK(ws.stage_in(&d_thr, threshold, (size_t)n_q));
+    // outputs are patched in place: host destinations are staged in full first
+    int64_t *d_rows = nullptr;
+    int32_t *d_count = nullptr;
+    if (is_device_pointer(out_rows)) {
+        d_rows = out_rows;
+    } else {
+        DS_CHECK(ws.stage_out(&d_rows, out_rows, (size_t)n_q * k));
+        DS_CUDA(cudaMemcpyAsync(d_rows, out_rows, (size_t)n_q * k * 8, cudaMemcpyHostToDevice, stream));
+    }
+    if (is_device_pointer(out_count)) {
+        d_count = out_count;
+    } else {
+        DS_CHECK(ws.stage_out(&d_count, out_count, (size_t)n_q));
+        DS_CUDA(cudaMemcpyAsync(d_count, out_count, (size_t)n_q * 4, cudaMemcpyHostToDevice, stream));
+    }
+    DS_CHECK(rescan_topn(ws, ix, qs, d_thr, flagged, k, d_rows, d_count));
+    return ws.finish_outputs();
+}
+
+int ds_topn(ds_index *index, int64_t n_q, const int64_t *q_row_ptr, const uint16_t *q_col_ids, const double *q_mx,
+            int32_t mx_mode, int32_t k, int64_t *out_rows, int32_t *out_count, float *out_kth_f32, int32_t *out_flags,
+            void *stream_) {
+    DS_CHECK(check_topn_args(index ? &index->ix : nullptr, n_q, q_row_ptr, q_col_ids, k));
+    if (out_rows == nullptr || out_count == nullptr) return fail(DS_ERR_BAD_ARG, "out_rows / out_count is NULL");
+    const Index &ix = index->ix;
+    if (ix.row_offset != 0 || ix.n_total != ix.n_truth)
+        return fail(DS_ERR_BAD_ARG, "ds_topn needs an unsharded index; use ds_topn_local / _merge / _rescan for shards");
+    DeviceGuard guard(ix.device);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (n_q == 0) return DS_OK;
+    Workspace ws(stream);
+    QuerySet qs;
+    DS_CHECK(prepare_queries(ws, ix, n_q, q_row_ptr, q_col_ids, q_mx, mx_mode, &qs));
+    const int m = ds_topn_retained(k);
+    double *d_score = nullptr, *d_thr = nullptr;
+    int64_t *d_row = nullptr, *d_rows = nullptr;
+    int32_t *d_count = nullptr, *d_flags = nullptr;
+    float *d_kth = nullptr;
+    int *d_flagged_count = nullptr;
+    DS_CHECK(ws.alloc(&d_score, (size_t)n_q * m));
+    DS_CHECK(ws.alloc(&d_row, (size_t)n_q * m));
+    DS_CHECK(ws.alloc(&d_thr, (size_t)n_q));
+    DS_CHECK(ws.alloc(&d_flagged_count, 1));
+    DS_CHECK(ws.stage_out(&d_rows, out_rows, (size_t)n_q * k));
+    DS_CHECK(ws.stage_out(&d_count, out_count, (size_t)n_q));
+    DS_CHECK(ws.stage_out(&d_kth, out_kth_f32, (size_t)n_q));
+    if (out_flags != nullptr) DS_CHECK(ws.stage_out(&d_flags, out_flags, (size_t)n_q));
+    else DS_CHECK(ws.alloc(&d_flags, (size_t)n_q));
+    DS_CUDA(cudaMemsetAsync(d_flagged_count, 0, 4, stream));
+    DS_CHECK(local_topn(ws, ix, qs, k, m, d_score, d_row));
+    DS_CHECK(merge_topn(stream, 1, n_q, k, m, ix.n_total, d_score, d_row, qs.d_mx, d_rows, d_count, d_kth, d_thr, d_flags, d_flagged_count));
+    int h_flagged = 0;
+    DS_CUDA(cudaMemcpyAsync(&h_flagged, d_flagged_count, 4, cudaMemcpyDeviceToHost, stream));
+    DS_CUDA(cudaStreamSynchronize(stream));
+    if (h_flagged > 0) {
+        std::vector<int32_t> flagged;
+        DS_CHECK(collect_flagged(stream, d_flags, n_q, &flagged));
+        DS_CHECK(rescan_topn(ws, ix, qs, d_thr, flagged, k, d_rows, d_count));
+    }
+    return ws.finish_outputs();
+}
+
+}  // extern "C"

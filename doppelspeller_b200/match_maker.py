@@ -1,0 +1,149 @@
+"""Drop-in `MatchMaker` (reference: /root/reference/doppelspeller/match_maker.py:74-203).
+
+Same constructor, same `get_closest_matches(row_number) -> list[title_id]`, same `top_n` attribute and
+the same exception when fewer than `top_n` rows exist - but the IDF-weighted Jaccard scan and the
+top-n selection run on the GPU (csrc/ds_topn.cu) for ALL rows of `data` at once: the reference's
+caller asks one row at a time (predict.py:126-127, feature_engineering_prepare.py:37-43), so the
+first call computes every row and later calls are served from the cached [Q, top_n] result.
+
+The host side below only assigns column ids and idf weights (match_maker.py:91-96,135-153).  Column
+ids and the order in which a truth row's weights are summed depend on python set iteration order in
+the reference (:144-147, :172-174); iterating the very same set objects in the same process
+reproduces both, which is what makes the results bit-identical.
+"""
+import logging
+import math
+from collections import Counter
+
+import numpy as np
+
+from . import _native as nat
+from .index import TruthIndex
+
+LOGGER = logging.getLogger(__name__)
+
+COLUMN_N_GRAMS = 'n_grams'      # constants.py:6
+COLUMN_TITLE_ID = 'title_id'    # constants.py:2
+TOO_FEW_ROWS_MESSAGE = 'top_matches.shape[0] != self.top_n'   # match_maker.py:189
+
+
+def _document_frequencies(n_gram_sets):
+    """common.py:145-147 get_n_grams_counter: document frequency over per-title n-gram sets."""
+    return Counter(x for y in n_gram_sets for x in set(y))
+
+
+def _rows_to_csr(rows, encoding):
+    ptr = np.zeros(len(rows) + 1, dtype=np.int64)
+    cols = []
+    for i, value in enumerate(rows):
+        cols.extend(encoding[x] for x in value)     # the set's own iteration order (match_maker.py:172-174)
+        ptr[i + 1] = len(cols)
+    return ptr, np.array(cols, dtype=np.uint16)
+
+
+class MatchMaker:
+    """
+    :param data: (dataframe) titles to find the closest truth titles for (column `n_grams`: set of str)
+    :param truth_data: (dataframe) the "truth" database (columns `n_grams`, `title_id`)
+    :param top_n: (int) number of nearest titles to fetch
+    :param device: CUDA device ordinal (default: torch's current device)
+    :param mx_mode: how `max_intersection_possible` is summed (match_maker.py:197): the default follows
+        CPython >= 3.12's compensated builtin sum(), DS_MX_NAIVE the plain sum of older interpreters
+    """
+
+    def __init__(self, data, truth_data, top_n, device=None, mx_mode=nat.DS_MX_PY312_COMPENSATED):
+        self.top_n = top_n
+        self.mx_mode = mx_mode
+        LOGGER.info(f'[{self.__class__.__name__}] Loading pre-requisite data!')
+        data_n_grams = list(data[COLUMN_N_GRAMS])
+        truth_n_grams = list(truth_data[COLUMN_N_GRAMS])
+
+        self.n_grams_counter = _document_frequencies(data_n_grams)                 # :91
+        self.n_grams_counter_truth = _document_frequencies(truth_n_grams)          # :92
+        self.number_of_truth_titles = len(truth_data)                              # :93
+        n_truth = self.number_of_truth_titles
+        self.idf_s_mapping = {key: math.log(n_truth / count)                       # :94, :135-142
+                              for key, count in self.n_grams_counter_truth.items()}
+        self.max_idf_value = max(self.idf_s_mapping.values())                      # :95
+        all_n_grams = set(list(self.n_grams_counter.keys()) + list(self.n_grams_counter_truth.keys()))   # :144-147
+        self.n_grams_decoding = {index: n_gram for index, n_gram in enumerate(all_n_grams)}
+        self.n_grams_encoding = {v: k for k, v in self.n_grams_decoding.items()}
+        if len(self.n_grams_encoding) > 65535:
+            raise Exception(f'{len(self.n_grams_encoding)} distinct n-grams: more than the 65535 u16 column ids')
+        idf64 = np.array([self.idf_s_mapping.get(self.n_grams_decoding[i], self.max_idf_value)   # :151, :180-181
+                          for i in range(len(self.n_grams_decoding))], dtype=np.float64)
+
+        t_ptr, t_cols = _rows_to_csr(truth_n_grams, self.n_grams_encoding)         # :167-178
+        q_ptr, q_cols = _rows_to_csr(data_n_grams, self.n_grams_encoding)          # :155-165
+        self.truth_data = truth_data.loc[:, [COLUMN_TITLE_ID]]                     # :104
+        self._init_device(idf64, t_ptr, t_cols, q_ptr, q_cols, device)
+        LOGGER.info(f'[{self.__class__.__name__}] Loaded pre-requisite data!')
+
+    @classmethod
+    def from_encoded(cls, idf64_by_col, t_row_ptr, t_col_ids, q_row_ptr, q_col_ids, title_ids, top_n, device=None,
+                     mx_mode=nat.DS_MX_PY312_COMPENSATED, sums=None):
+        """Builds a MatchMaker from already assigned column ids (fixtures, synthetic data, the canonical
+        encoder in `encode.py`): truth / query CSR with u16 column ids, idf per column, title id per truth row."""
+        self = cls.__new__(cls)
+        self.top_n = top_n
+        self.mx_mode = mx_mode
+        self.number_of_truth_titles = int(t_row_ptr.shape[0]) - 1
+        self.truth_data = None
+        self._title_ids = np.asarray(title_ids)
+        self._init_device(np.ascontiguousarray(idf64_by_col, dtype=np.float64), t_row_ptr, t_col_ids, q_row_ptr, q_col_ids,
+                          device, sums=sums)
+        return self
+
+    def _init_device(self, idf64, t_ptr, t_cols, q_ptr, q_cols, device, sums=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise nat.DoppelSpellerError(-2, 'no CUDA device available (doppelspeller_b200 has no CPU fallback)')
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self._index = TruthIndex(t_ptr, t_cols, idf64, sums=sums, device=self.device)
+        self._q_ptr = np.ascontiguousarray(q_ptr, dtype=np.int64)
+        self._q_cols = np.ascontiguousarray(q_cols, dtype=np.uint16)
+        self._rows = None
+        self._count = None
+        self._flags = None
+
+    @property
+    def sums_matrix_truth(self):
+        """match_maker.py:100,:174 - computed on the device in the reference's accumulation order."""
+        return self._index.sums()
+
+    def _compute_all(self):
+        rows, count, _, flags = self._index.topn(self._q_ptr, self._q_cols, self.top_n, mx_mode=self.mx_mode,
+                                                 with_details=True)
+        self._rows, self._count, self._flags = rows, count, flags
+
+    def closest_rows(self):
+        """All queries at once: (truth row indexes int64[Q, top_n] in descending row order, count[Q])."""
+        if self._rows is None:
+            self._compute_all()
+        return self._rows, self._count
+
+    def _title_ids_of(self, top_matches):
+        if self.truth_data is not None:
+            return self.truth_data.loc[top_matches, COLUMN_TITLE_ID].tolist()      # match_maker.py:190
+        return self._title_ids[top_matches].tolist()
+
+    def get_closest_matches(self, row_number):
+        """Given the "row_number" of the data, gets the closest (self.top_n) titles in the truth data
+        (match_maker.py:192-203)."""
+        rows, count = self.closest_rows()
+        top_matches = rows[row_number, :count[row_number]]
+        if top_matches.shape[0] != self.top_n:
+            raise Exception(TOO_FEW_ROWS_MESSAGE)
+        return self._title_ids_of(top_matches)
+
+    def get_closest_matches_batch(self):
+        """[Q, top_n] title ids for every row of the data (vectorised form of the caller's loop)."""
+        rows, count = self.closest_rows()
+        if (count != self.top_n).any():
+            raise Exception(TOO_FEW_ROWS_MESSAGE)
+        flat = rows.reshape(-1)
+        if self.truth_data is not None:
+            ids = self.truth_data.loc[flat, COLUMN_TITLE_ID].to_numpy()
+        else:
+            ids = self._title_ids[flat]
+        return ids.reshape(rows.shape)

@@ -1,0 +1,109 @@
+"""Top-n search over a truth DB sharded across the GPUs of one box.
+
+One process per GPU (torch.distributed, NCCL over NVLink).  Rank r holds the contiguous truth rows
+[offsets[r], offsets[r+1]) as its own `TruthIndex`; the IDF weights are global (computed over the
+whole DB before sharding) and the queries are replicated.  The reference's selection rule needs one
+global quantity in the middle - the k-th largest float32 score - so the path has exactly one
+exchange step:
+
+    phase 1  local scan           -> best m candidates per query  (score64, global row)
+    all_gather of [Q, m] scores + rows over the shards            (the only collective on the path)
+    phase 2  merge (replicated)   -> global k-th key, threshold, final rows or a RESCAN flag
+    phase 3  rescan (flagged only) + all_gather of the [F, k] local answers, highest shard first
+
+Without sharding (one rank) no collective is issued at all.
+"""
+import numpy as np
+
+from . import _native as nat
+
+
+def shard_offsets(n_total, n_shards):
+    """Contiguous ascending row ranges: shard r owns [off[r], off[r+1])."""
+    base, extra = divmod(int(n_total), int(n_shards))
+    sizes = [base + (1 if r < extra else 0) for r in range(n_shards)]
+    return np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+
+
+def slice_truth_csr(t_row_ptr, t_col_ids, r0, r1):
+    ptr = t_row_ptr[r0:r1 + 1]
+    cols = t_col_ids[ptr[0]:ptr[-1]]
+    return np.ascontiguousarray(ptr - ptr[0]), np.ascontiguousarray(cols)
+
+
+def combine_rescans(per_shard_rows, per_shard_count, k):
+    """Final rows of the re-scanned queries: every shard reports its k highest qualifying rows
+    (descending); shards are contiguous ascending ranges, so the answer is the concatenation from the
+    highest shard down, cut at k.  per_shard_rows [S, F, k], per_shard_count [S, F] (torch tensors)."""
+    import torch
+    n_shards, n_f, _ = per_shard_rows.shape
+    out = torch.full((n_f, k), -1, dtype=torch.int64, device=per_shard_rows.device)
+    filled = torch.zeros(n_f, dtype=torch.int64, device=per_shard_rows.device)
+    for s in range(n_shards - 1, -1, -1):
+        cnt = per_shard_count[s].to(torch.int64)
+        take = torch.minimum(cnt, k - filled)
+        for f in torch.nonzero(take > 0).flatten().tolist():
+            t = int(take[f])
+            out[f, int(filled[f]):int(filled[f]) + t] = per_shard_rows[s, f, :t]
+        filled = filled + take
+    return out, filled.to(torch.int32)
+
+
+class GpuShard:
+    """Kernel backend of one rank: wraps a TruthIndex, moves the replicated queries to its device once."""
+
+    def __init__(self, index, q_row_ptr, q_col_ids, mx_mode=nat.DS_MX_PY312_COMPENSATED):
+        import torch
+        self.index = index
+        self.device = torch.device('cuda', index.device)
+        self.q_ptr = torch.as_tensor(np.ascontiguousarray(q_row_ptr, dtype=np.int64)).to(self.device)
+        self.q_cols = torch.as_tensor(np.ascontiguousarray(q_col_ids, dtype=np.uint16)).to(self.device)
+        self.mx_mode = mx_mode
+        self.n_total = index.n_total
+
+    def local(self, k):
+        return self.index.topn_local(self.q_ptr, self.q_cols, k, mx_mode=self.mx_mode)
+
+    def merge(self, all_score, all_row, k, q_mx):
+        from .index import topn_merge
+        return topn_merge(all_score, all_row, k, self.n_total, q_mx=q_mx, device=self.index.device)
+
+    def rescan(self, q_mx, threshold, flags, k):
+        import torch
+        n_q = self.q_ptr.shape[0] - 1
+        rows = torch.full((n_q, k), -1, dtype=torch.int64, device=self.device)
+        count = torch.zeros(n_q, dtype=torch.int32, device=self.device)
+        self.index.topn_rescan(self.q_ptr, self.q_cols, q_mx, threshold, flags, k, rows, count)
+        return rows, count
+
+
+def _all_gather(tensor, group, world):
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return tensor.unsqueeze(0)
+    out = torch.empty((world,) + tuple(tensor.shape), dtype=tensor.dtype, device=tensor.device)
+    dist.all_gather_into_tensor(out, tensor.contiguous(), group=group)
+    return out
+
+
+def sharded_topn(shard, k, group=None):
+    """Runs the three phases on this rank's `shard` (GpuShard or any object with local / merge / rescan).
+    Returns (rows int64[Q,k] global truth rows in descending order, count int32[Q], flags int32[Q]) -
+    identical on every rank."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    score, row, mx = shard.local(k)
+    all_score = _all_gather(score, group, world)
+    all_row = _all_gather(row, group, world)
+    rows, count, _, threshold, flags = shard.merge(all_score, all_row, k, mx)
+    flagged = torch.nonzero((flags & nat.DS_FLAG_RESCAN) != 0).flatten()
+    if flagged.numel() > 0:          # the same set on every rank: merge inputs are replicated
+        local_rows, local_count = shard.rescan(mx, threshold, flags, k)
+        per_rows = _all_gather(local_rows[flagged], group, world)
+        per_count = _all_gather(local_count[flagged], group, world)
+        fixed_rows, fixed_count = combine_rescans(per_rows, per_count, k)
+        rows[flagged] = fixed_rows
+        count[flagged] = fixed_count
+    return rows, count, flags

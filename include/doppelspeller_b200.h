@@ -1,0 +1,180 @@
+/*
+ * doppelspeller_b200.h - C ABI of the B200-native DoppelSpeller hot path.
+ *
+ * The reference (mhaseebtariq/doppel-speller) is pure Python + numba: it has no FFI of its own.  The
+ * drop-in boundary is therefore the set of Python call signatures listed in SURVEY.md 8(b); this
+ * header is the C ABI a binding for those signatures talks to (ctypes stub: INTEGRATION.md and
+ * doppelspeller_b200/_native.py).  Each entry point names the reference interface it replaces.
+ *
+ * Conventions
+ *   - every function returns DS_OK (0) or a negative ds_status; ds_last_error() gives the
+ *     thread-local message.  No exceptions cross the boundary.  There is no CPU fallback: without a
+ *     usable sm_100 device every compute entry point fails with DS_ERR_CUDA.
+ *   - data pointers may be DEVICE pointers (used in place, call is asynchronous on `stream`) or HOST
+ *     pointers (staged through the library's own device workspace; when an OUTPUT pointer is a host
+ *     pointer the call synchronises `stream` before it returns).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).
+ *   - all buffers are caller-owned; the library owns only the opaque ds_index and per-call workspace
+ *     it releases (stream-ordered) before returning.
+ */
+#ifndef DOPPELSPELLER_B200_H
+#define DOPPELSPELLER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DS_VERSION 100          /* 0.1.0 */
+#define DS_N_WORDS 15           /* settings.py:65  NUMBER_OF_WORDS_FEATURES */
+#define DS_N_FEATURES 66        /* feature_engineering.py:67  FEATURES_COUNT */
+#define DS_MAX_TITLE 255        /* settings.py:68  MAX_CHARACTERS_ALLOWED_IN_THE_TITLE */
+#define DS_MAX_TOP_N 1024       /* largest supported top_n */
+
+typedef enum ds_status {
+    DS_OK = 0,
+    DS_ERR_BAD_ARG = -1,
+    DS_ERR_CUDA = -2,
+    DS_ERR_NO_MEMORY = -3,
+    DS_ERR_UNSUPPORTED = -4,    /* e.g. n_vocab > 65535, top_n > DS_MAX_TOP_N */
+    DS_ERR_TOO_FEW_ROWS = -5    /* reserved: ds_topn reports short results through out_count instead and the
+                                   binding raises the reference's exception (match_maker.py:188-189) */
+} ds_status;
+
+/* ds_topn out_flags bits */
+#define DS_FLAG_RESCAN 1        /* more than the retained candidates qualified: exact re-scan was taken */
+#define DS_FLAG_FEW_POSITIVE 2  /* fewer than top_n positive scores: the last top_n truth rows were returned */
+
+/* sum mode of the per-query denominator term `max_intersection_possible` (match_maker.py:197) */
+#define DS_MX_PY312_COMPENSATED 0   /* CPython >= 3.12 builtin sum(): Neumaier compensated (as executed today) */
+#define DS_MX_NAIVE 1               /* CPython <= 3.11 builtin sum(): plain sequential float64 */
+
+typedef struct ds_index ds_index;
+
+int ds_version(void);
+const char *ds_last_error(void);
+/* number of CUDA kernels this library has launched in the calling process (bench.py gpu_launches) */
+int64_t ds_kernel_launches(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * ds_index_create  -  replaces the truth-side half of MatchMaker.__init__ (match_maker.py:97-109:
+ * `_construct_truth_data_sparse_matrix` :167-178, `_get_matrix_truth_non_zero_columns_and_values`
+ * :122-133) once the host has assigned column ids (:144-147) and idf weights (:135-142).
+ *
+ *   n_truth, n_vocab     truth rows of THIS shard / columns (n_vocab <= 65535)
+ *   t_row_ptr [n_truth+1], t_col_ids [nnz]
+ *                        CSR of the truth rows; the column order inside a row is the order in which
+ *                        the reference accumulates `sums_matrix_truth` (python set iteration order,
+ *                        :172-174).  Rows must not contain duplicates.
+ *   idf64_by_col [n_vocab]  float64 idf (query-only n-grams carry max idf, :151,:180-181); the float32
+ *                        weights are derived as (float)idf64 exactly like numpy's astype (:130,:152).
+ *   sums_truth_f32       optional [n_truth] precomputed `sums_matrix_truth`; NULL => computed on the
+ *                        device as the sequential float32 sum in the given column order.
+ *   global_row_offset    index of this shard's first row in the whole truth DB (multi-GPU sharding)
+ *   n_truth_total        rows of the whole truth DB (== n_truth when not sharded)
+ * ------------------------------------------------------------------------------------------------- */
+int ds_index_create(ds_index **out, int device, int64_t n_truth, int32_t n_vocab, const int64_t *t_row_ptr,
+                    const uint16_t *t_col_ids, const double *idf64_by_col, const float *sums_truth_f32,
+                    int64_t global_row_offset, int64_t n_truth_total, void *stream);
+int ds_index_destroy(ds_index *index);
+/* copies the device-resident `sums_matrix_truth` (float32 [n_truth]) to `out` (host or device) */
+int ds_index_get_sums(const ds_index *index, float *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * ds_topn  -  replaces `[MatchMaker.get_closest_matches(row) for row in rows]`
+ * (match_maker.py:192-203 = python sum :197 + fast_jaccard :16-50 + fast_arg_top_k :53-71), without
+ * the title_id lookup of :190 (the binding maps rows to ids).
+ *
+ *   q_row_ptr [n_q+1], q_col_ids   CSR of the query rows' column ids (any order, no duplicates;
+ *                        zero-weight columns may be present, they are no-ops like in the lil matrix)
+ *   q_mx                 optional [n_q] float64 `max_intersection_possible`; NULL => computed on the
+ *                        device from idf64_by_col over the ascending column ids with `mx_mode`
+ *   k                    top_n
+ *   out_rows [n_q*k]     GLOBAL truth row indexes, DESCENDING row index (the reference's order,
+ *                        match_maker.py:71); -1 padded when fewer than k rows exist
+ *   out_count [n_q]      rows written per query (== k unless the DB has fewer than k rows)
+ *   out_kth_f32          optional [n_q] k-th largest float32-rounded positive score (0 when fewer)
+ *   out_flags            optional [n_q] DS_FLAG_* bits
+ * ------------------------------------------------------------------------------------------------- */
+int ds_topn(ds_index *index, int64_t n_q, const int64_t *q_row_ptr, const uint16_t *q_col_ids,
+            const double *q_mx, int32_t mx_mode, int32_t k, int64_t *out_rows, int32_t *out_count,
+            float *out_kth_f32, int32_t *out_flags, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Sharded form of ds_topn (truth rows split over GPUs, one ds_index per shard).
+ *   phase 1  ds_topn_local : every shard scans its rows and returns its best `m` candidates per query
+ *            as (score64, global row), ordered by score descending (ties: higher row first);
+ *            unused slots carry score -1 / row -1.  `m` = ds_topn_retained(k).
+ *   (the caller all-gathers out_score / out_row over the shards - NCCL all_gather)
+ *   phase 2  ds_topn_merge : every shard derives the global k-th key, the threshold and the final
+ *            rows from the gathered [n_shards, n_q, m] candidates; queries whose candidate lists
+ *            cannot prove the answer are reported in out_flags (DS_FLAG_RESCAN) with the threshold in
+ *            out_threshold, and are resolved by
+ *   phase 3  ds_topn_rescan : exact re-scan of the local shard for the flagged queries with the known
+ *            global threshold, returning the k highest local rows (descending) that reach it.
+ * ------------------------------------------------------------------------------------------------- */
+int32_t ds_topn_retained(int32_t k);
+int ds_topn_local(ds_index *index, int64_t n_q, const int64_t *q_row_ptr, const uint16_t *q_col_ids,
+                  const double *q_mx, int32_t mx_mode, int32_t k, double *out_score, int64_t *out_row,
+                  double *out_mx, void *stream);
+int ds_topn_merge(int32_t n_shards, int64_t n_q, int32_t k, int64_t n_truth_total, const double *all_score,
+                  const int64_t *all_row, const double *q_mx /* nullable: out_mx of ds_topn_local */,
+                  int64_t *out_rows, int32_t *out_count, float *out_kth_f32, double *out_threshold,
+                  int32_t *out_flags, int device, void *stream);
+int ds_topn_rescan(ds_index *index, int64_t n_q, const int64_t *q_row_ptr, const uint16_t *q_col_ids,
+                   const double *q_mx, const double *threshold, const int32_t *flags, int32_t k,
+                   int64_t *out_rows, int32_t *out_count, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * ds_indel_ratio_u8  -  replaces fast_levenshtein_ratio (feature_engineering.py:25-63) over n pairs.
+ *   a, b [n, stride]  uint8 code rows (the reference's zero padded [P,255] layout: stride 255)
+ *   la, lb [n]        lengths (uint8, like the reference's arrays)
+ *   out_ratio [n]     uint8 ratio exactly as the reference executes it: (100*(L-d))/L with the
+ *                     uint8-wrapping distance d; 0 when la+lb == 0
+ *   out_dist          optional [n] uint16 (the uint8-wrapped distance d)
+ * ------------------------------------------------------------------------------------------------- */
+int ds_indel_ratio_u8(const uint8_t *a, const uint8_t *b, int64_t stride, const uint8_t *la, const uint8_t *lb,
+                      int64_t n, uint8_t *out_ratio, uint16_t *out_dist, void *stream);
+
+/* Same arithmetic on a compact title table: pair p compares table_a[idx_a[p]] with table_b[idx_b[p]];
+ * a table is (bytes, offsets[n_titles+1]); titles longer than 255 bytes are truncated like
+ * FeatureEngineering.encode_title does.  This is the B200 layout (no [P,255] materialisation). */
+int ds_indel_ratio_pairs(const uint8_t *bytes_a, const int64_t *offsets_a, int64_t n_titles_a,
+                         const uint8_t *bytes_b, const int64_t *offsets_b, int64_t n_titles_b,
+                         const int32_t *idx_a, const int32_t *idx_b, int64_t n, uint8_t *out_ratio,
+                         uint16_t *out_dist, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * ds_levenshtein_ratio_pairs  -  replaces common.levenshtein_ratio (common.py:161-162) over n pairs of
+ * raw byte strings: int(round(ratio*100)) with python-levenshtein's ratio = (la+lb-indel)/(la+lb)
+ * (true, non-wrapping InDel distance; 1.0 for two empty strings) and Python's round-half-even.
+ * Strings are given as a compact table like above.  out [n] int32 in 0..100.
+ * ------------------------------------------------------------------------------------------------- */
+int ds_levenshtein_ratio_pairs(const uint8_t *bytes_a, const int64_t *offsets_a, int64_t n_titles_a,
+                               const uint8_t *bytes_b, const int64_t *offsets_b, int64_t n_titles_b,
+                               const int32_t *idx_a, const int32_t *idx_b, int64_t n, int32_t *out,
+                               void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * ds_construct_features  -  replaces the construct_features gufunc (feature_engineering.py:69-169),
+ * layout '(),(),(l),(l),(m),(),(),(n)->(n)' with l = stride, m = 15, n = 66.
+ *   la, lb [P] uint8; a, b [P, stride] uint8 codes; counts [P,15] uint32 truth-word document
+ *   frequencies; space_code; n_truth (uint32, number_of_truth_titles); out [P,66] float32.
+ * ------------------------------------------------------------------------------------------------- */
+int ds_construct_features(const uint8_t *la, const uint8_t *lb, const uint8_t *a, const uint8_t *b,
+                          int64_t stride, const uint32_t *counts, uint8_t space_code, uint32_t n_truth,
+                          int64_t n_pairs, float *out, void *stream);
+
+/* Compact form: titles in (bytes, offsets) tables, truth-word counts per TRUTH TITLE [n_truth_titles,15],
+ * pair p = (idx_a[p], idx_b[p]).  Same arithmetic, 373 instead of 836 bytes of traffic per pair. */
+int ds_construct_features_pairs(const uint8_t *bytes_a, const int64_t *offsets_a, int64_t n_titles_a,
+                                const uint8_t *bytes_b, const int64_t *offsets_b, int64_t n_titles_b,
+                                const uint32_t *counts_b, const int32_t *idx_a, const int32_t *idx_b,
+                                uint8_t space_code, uint32_t n_truth, int64_t n_pairs, float *out,
+                                void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DOPPELSPELLER_B200_H */

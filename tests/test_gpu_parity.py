@@ -1,0 +1,263 @@
+"""GPU: parity of the CUDA path (through the C ABI) with the golden vectors minted from the reference
+and with the CPU oracle on seeded inputs.  Bit-exact for rows / distances / integer features; 1e-6
+relative for the float32 idf / rank features (north_star tolerance)."""
+import numpy as np
+import pytest
+
+from tests.conftest import features_equal, oracle_index_from_encoded, oracle_index_from_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _match_maker(enc, k, title_ids=None, **kw):
+    from doppelspeller_b200.match_maker import MatchMaker
+    n_truth = int(enc['t_ptr'].shape[0]) - 1
+    ids = np.arange(n_truth) if title_ids is None else title_ids
+    return MatchMaker.from_encoded(enc['idf64'], enc['t_ptr'], enc['t_cols'], enc['q_ptr'], enc['q_cols'], ids, k, **kw)
+
+
+def _golden_enc(g):
+    return dict(idf64=g['w64'], t_ptr=g['t_ptr'], t_cols=g['t_cols'], q_ptr=g['q_ptr'], q_cols=g['q_cols'])
+
+
+# ------------------------------------------------------------------ K1: candidates
+def test_sums_match_reference(golden_matchmaker):
+    mm = _match_maker(_golden_enc(golden_matchmaker), 10)
+    assert np.array_equal(mm.sums_matrix_truth.view(np.uint32), golden_matchmaker['sums'].view(np.uint32))
+
+
+@pytest.mark.parametrize('k,key', [(10, 'top10_rows'), (100, 'top100_rows')])
+def test_candidates_match_reference_example(golden_matchmaker, k, key):
+    g = golden_matchmaker
+    mm = _match_maker(_golden_enc(g), k, title_ids=g['title_ids'])
+    rows, count = mm.closest_rows()
+    assert (count == k).all()
+    assert np.array_equal(rows, g[key].astype(np.int64))
+    # the drop-in call: title ids in the reference's order
+    for q in (0, 1, 17, 999):
+        assert mm.get_closest_matches(q) == g['title_ids'][g[key][q]].tolist()
+
+
+@pytest.mark.parametrize('n_truth,n_q,k,seed', [(20000, 1500, 10, 1), (20000, 700, 100, 2), (3000, 300, 1, 3),
+                                                 (50000, 400, 10, 4), (700, 100, 512, 5)])
+def test_candidates_match_oracle_synthetic(n_truth, n_q, k, seed):
+    from doppelspeller_b200 import encode, synthetic
+    from oracle import oracle
+    truth = synthetic.generate_truth_titles(n_truth, seed=seed)
+    test, _ = synthetic.generate_test_titles(truth, n_q, seed=seed + 100)
+    enc = encode.encode_canonical(test, truth)
+    rows, count, kth, flags = _match_maker(enc, k)._index.topn(enc['q_ptr'], enc['q_cols'], k, with_details=True)
+    want_rows, want_count, want_kth = oracle.topn(oracle_index_from_encoded(enc), k)
+    assert np.array_equal(count, want_count)
+    assert np.array_equal(rows, want_rows)
+    assert np.array_equal(kth, want_kth)
+
+
+def _tiny_case(truth_sets, query_sets, n_vocab):
+    """Hand-built index: column ids given directly, idf from document frequencies."""
+    import math
+    n = len(truth_sets)
+    df = np.zeros(n_vocab)
+    for s in truth_sets:
+        for c in s:
+            df[c] += 1
+    idf = np.array([math.log(n / d) if d > 0 else 0.0 for d in df])
+    idf[df == 0] = idf.max()
+
+    def csr(sets):
+        ptr = np.zeros(len(sets) + 1, dtype=np.int64)
+        np.cumsum([len(s) for s in sets], out=ptr[1:])
+        cols = np.array([c for s in sets for c in s], dtype=np.uint16)
+        return ptr, cols
+    t_ptr, t_cols = csr(truth_sets)
+    q_ptr, q_cols = csr(query_sets)
+    return dict(idf64=idf, t_ptr=t_ptr, t_cols=t_cols, q_ptr=q_ptr, q_cols=q_cols)
+
+
+def _check_against_oracle(enc, k):
+    from oracle import oracle
+    rows, count, kth, flags = _match_maker(enc, k)._index.topn(enc['q_ptr'], enc['q_cols'], k, with_details=True)
+    want_rows, want_count, want_kth = oracle.topn(oracle_index_from_encoded(enc), k)
+    assert np.array_equal(count, want_count)
+    assert np.array_equal(rows, want_rows)
+    assert np.array_equal(kth, want_kth)
+    return rows, count, flags
+
+
+def test_edge_massive_ties_and_dropped_argmax():
+    # 400 identical truth rows tie at the k-th place: more than the retained list can hold -> exact rescan,
+    # and (like the reference) the k HIGHEST rows win even though an earlier row scores higher
+    rng = np.random.default_rng(7)
+    truth = [[0, 1, 2, 3]] + [[0, 1, 5 + i % 3] for i in range(30)] + [[0, 1, 9]] * 400 + [[20 + i, 21 + i] for i in range(50)]
+    queries = [[0, 1, 2, 3], [0, 1, 9], [0, 1], [0, 1, 9, 30, 31], [40, 41, 42]]
+    rows, count, flags = _check_against_oracle(_tiny_case(truth, queries, 80), 10)
+    assert (flags & 1).any()
+    del rng
+
+
+def test_edge_fewer_than_k_positives_returns_last_rows():
+    truth = [[i, i + 1] for i in range(0, 200, 2)]
+    queries = [[0, 1], [500], [4, 5, 8]]
+    enc = _tiny_case(truth, queries, 600)
+    rows, count, flags = _check_against_oracle(enc, 10)
+    assert rows[1].tolist() == list(range(99, 89, -1))
+    assert (flags & 2).all()
+
+
+def test_edge_fewer_rows_than_k_raises_like_reference():
+    truth = [[0, 1], [1, 2], [2, 3]]
+    enc = _tiny_case(truth, [[0, 1]], 8)
+    rows, count, flags = _check_against_oracle(enc, 5)
+    assert count[0] == 3
+    mm = _match_maker(enc, 5)
+    with pytest.raises(Exception, match=r'top_matches.shape\[0\] != self.top_n'):
+        mm.get_closest_matches(0)
+
+
+def test_edge_empty_and_ragged_queries():
+    truth = [[i % 7, 7 + i % 5, 12 + i % 3] for i in range(300)] + [list(range(40, 140))]
+    queries = [[], [0], list(range(40, 140)), [0, 7, 12], list(range(0, 15))]
+    _check_against_oracle(_tiny_case(truth, queries, 150), 10)
+    _check_against_oracle(_tiny_case(truth, queries, 150), 100)
+
+
+def test_edge_near_ties_inside_float_buffer():
+    # many rows whose scores differ in the last bits: exercises the 1e-6 band and the retained-list flag
+    rng = np.random.default_rng(11)
+    truth = [sorted(rng.choice(60, size=int(rng.integers(3, 9)), replace=False).tolist()) for _ in range(4000)]
+    queries = [sorted(rng.choice(60, size=int(rng.integers(2, 12)), replace=False).tolist()) for _ in range(200)]
+    _check_against_oracle(_tiny_case(truth, queries, 60), 10)
+    _check_against_oracle(_tiny_case(truth, queries, 60), 100)
+
+
+def test_device_resident_inputs_match_host_inputs(golden_matchmaker):
+    import torch
+    g = golden_matchmaker
+    mm = _match_maker(_golden_enc(g), 10)
+    q_ptr = torch.as_tensor(g['q_ptr']).cuda()
+    q_cols = torch.as_tensor(g['q_cols']).cuda()
+    rows, count = mm._index.topn(q_ptr, q_cols, 10)
+    assert rows.is_cuda
+    assert np.array_equal(rows.cpu().numpy(), g['top10_rows'].astype(np.int64))
+
+
+def test_sharded_phases_on_one_gpu_match_single_index(golden_matchmaker):
+    """Truth split into 3 shards held on the same GPU: local -> stack -> merge -> rescan -> combine."""
+    import torch
+    from doppelspeller_b200 import sharded
+    from doppelspeller_b200.index import TruthIndex, topn_merge
+    g = golden_matchmaker
+    n = int(g['t_ptr'].shape[0]) - 1
+    for k, key in ((10, 'top10_rows'), (100, 'top100_rows')):
+        offs = sharded.shard_offsets(n, 3)
+        shards = []
+        for r in range(3):
+            ptr, cols = sharded.slice_truth_csr(g['t_ptr'], g['t_cols'], int(offs[r]), int(offs[r + 1]))
+            shards.append(TruthIndex(ptr, cols, g['w64'], row_offset=int(offs[r]), n_total=n))
+        local = [s.topn_local(g['q_ptr'], g['q_cols'], k) for s in shards]
+        all_score = np.stack([l[0] for l in local])
+        all_row = np.stack([l[1] for l in local])
+        rows, count, kth, thr, flags = topn_merge(all_score, all_row, k, n, q_mx=local[0][2])
+        flagged = np.nonzero(flags & 1)[0]
+        if flagged.size:
+            per_rows, per_count = [], []
+            for s in shards:
+                lr = np.full((len(flags), k), -1, dtype=np.int64)
+                lc = np.zeros(len(flags), dtype=np.int32)
+                s.topn_rescan(g['q_ptr'], g['q_cols'], local[0][2], thr, flags, k, lr, lc)
+                per_rows.append(lr[flagged])
+                per_count.append(lc[flagged])
+            fixed, fixed_count = sharded.combine_rescans(torch.as_tensor(np.stack(per_rows)),
+                                                         torch.as_tensor(np.stack(per_count)), k)
+            rows[flagged] = fixed.numpy()
+            count[flagged] = fixed_count.numpy()
+        assert np.array_equal(rows, g[key].astype(np.int64))
+        assert (count == k).all()
+
+
+# ------------------------------------------------------------------ K2 / K3: pair scoring
+def test_indel_ratio_matches_reference(golden_pairs):
+    from doppelspeller_b200 import feature_engineering as fe
+    g = golden_pairs
+    got, dist = fe.fast_levenshtein_ratio_batch(g['ratio_a'], g['ratio_b'], g['ratio_la'].astype(np.uint8),
+                                                g['ratio_lb'].astype(np.uint8), with_distance=True)
+    keep = g['ratio_la'] + g['ratio_lb'] > 0          # empty vs empty raises in the reference
+    assert np.array_equal(got[keep], g['ratio_out'][keep])
+    assert fe.fast_levenshtein_ratio(np.array([2] * 29 + [3] * 21, np.uint8), np.array([2] * 29 + [4] * 21, np.uint8)) == 58
+    with pytest.raises(ZeroDivisionError):
+        fe.fast_levenshtein_ratio(np.zeros(0, np.uint8), np.zeros(0, np.uint8))
+
+
+def test_indel_ratio_random_against_oracle():
+    from doppelspeller_b200 import feature_engineering as fe
+    from oracle import oracle
+    rng = np.random.default_rng(5)
+    n = 20000
+    la = rng.integers(0, 256, n).astype(np.uint8)
+    lb = rng.integers(0, 256, n).astype(np.uint8)
+    short = rng.random(n) < 0.7
+    la[short] = rng.integers(1, 60, short.sum())
+    lb[short] = rng.integers(1, 60, short.sum())
+    alpha = rng.integers(2, 38, n)
+    a = (rng.integers(0, 1 << 30, (n, 255)) % alpha[:, None]).astype(np.uint8)
+    b = (rng.integers(0, 1 << 30, (n, 255)) % alpha[:, None]).astype(np.uint8)
+    similar = rng.random(n) < 0.5
+    b[similar] = a[similar]
+    flips = rng.integers(0, 255, (n, 4))
+    for j in range(4):
+        b[np.arange(n), flips[:, j]] = rng.integers(0, 38, n)
+    wild = rng.random(n) < 0.02                        # codes outside the 38-symbol alphabet -> literal DP path
+    a[wild, 0] = 200
+    got = fe.fast_levenshtein_ratio_batch(a, b, la, lb)
+    want = oracle.indel_ratio_u8_batch(a, b, la, lb)
+    assert np.array_equal(got, want)
+
+
+def test_construct_features_matches_reference(golden_pairs):
+    from doppelspeller_b200 import feature_engineering as fe
+    g = golden_pairs
+    out = np.zeros((len(g['feat_la']), 66), dtype=np.float32)
+    ret = fe.construct_features(g['feat_la'], g['feat_lb'], g['feat_a'], g['feat_b'], g['feat_counts'], np.uint8(1),
+                                np.uint32(g['feat_n_truth']), np.zeros(66, np.uint8), out)
+    assert ret is out
+    assert features_equal(out, g['feat_out'])
+
+
+def test_construct_features_pairs_table_form(golden_pairs):
+    import torch
+    from doppelspeller_b200 import feature_engineering as fe
+    g = golden_pairs
+    titles = [str(t) for t in g['feat_titles']]
+    truths = [str(t) for t in g['feat_truths']]
+    n = len(titles)
+    idx = np.arange(n, dtype=np.int32)
+    got = fe.construct_features_pairs(fe.encode_titles(titles), fe.encode_titles(truths), g['feat_counts'], idx, idx, 1,
+                                      int(g['feat_n_truth']))
+    assert features_equal(got, g['feat_out'])
+    # device-resident padded layout
+    dev = [torch.as_tensor(g[key]).cuda() for key in ('feat_la', 'feat_lb', 'feat_a', 'feat_b')]
+    counts = torch.as_tensor(g['feat_counts'].view(np.int32)).cuda()
+    got_dev = fe.construct_features(dev[0], dev[1], dev[2], dev[3], counts, 1, int(g['feat_n_truth']))
+    assert features_equal(got_dev.cpu().numpy(), g['feat_out'])
+
+
+def test_levenshtein_ratio_and_prematch_against_oracle(example_titles):
+    from doppelspeller_b200 import common, predict
+    from oracle import oracle
+    rng = np.random.default_rng(9)
+    truth, test = example_titles['truth_titles'], example_titles['test_titles']
+    xs = [test[i] for i in rng.integers(0, len(test), 3000)]
+    ys = [truth[i] for i in rng.integers(0, len(truth), 3000)]
+    for i in range(0, 3000, 3):                         # near duplicates: the > 94 region and the token-sort branch
+        ys[i] = xs[i][:-1] if i % 2 else ' '.join(reversed(xs[i].split()))
+    xs += ['', 'abc', 'ab', 'abcdefgh', 'x\ty']
+    ys += ['', 'abc', 'abcd', 'abcdefgx', 'x y']
+    got = common.levenshtein_ratio_batch(xs, ys)
+    want = np.array([oracle.levenshtein_ratio(x, y) for x, y in zip(xs, ys)])
+    assert np.array_equal(got, want)
+    assert common.levenshtein_ratio('coolblu bv', 'coolblue bv') == 95
+    assert common.levenshtein_token_sort_ratio('bv coolblue', 'coolblue bv') == 100
+    xs2, ys2 = xs[:-5], ys[:-5]
+    got = predict.get_levenshtein_ratios(xs2, ys2)
+    want = np.array([oracle.prematch_ratio(x, y) for x, y in zip(xs2, ys2)])
+    assert np.array_equal(got, want)
