@@ -1,0 +1,380 @@
+"""bench.py - headline benchmark of the B200-native DoppelSpeller hot path.
+
+Workload (BASELINE.json configs[2], "C3"): synthetic 100,000 test titles x 500,000 truth titles of the
+example data set's length / trigram statistics, nearest-n = 10 IDF-weighted Jaccard top-n.  A "step" is
+one pass of the hot path over the whole query batch: every (query, truth) pair scored, the reference's
+selection rule applied, [Q, 10] candidate rows produced.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+`value`   whole-job titles/s with the query CSR already resident in HBM (device-timed, CUDA events,
+          max over ranks);  `e2e` the same through the public API with pinned HOST buffers (H2D of the
+          queries and D2H of the candidate rows inside the timed region).
+N > 1     (torchrun) the truth rows are sharded over the ranks; phases local -> all_gather -> merge
+          (doppelspeller_b200/sharded.py); total work is fixed -> "scaling": "strong".
+--impl reference   times the CPU port of the reference path (oracle/, all host threads) on a bounded
+          sample of the same workload; rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'titles matched/sec vs 500k truth'
+UNIT = 'titles/s'
+
+
+def log(*args):
+    print(*args, file=sys.stderr, flush=True)
+
+
+def build_workload(n_queries, n_truth):
+    from doppelspeller_b200 import encode, synthetic
+    t0 = time.time()
+    truth = synthetic.generate_truth_titles(n_truth)
+    test, _ = synthetic.generate_test_titles(truth, n_queries)
+    enc = encode.encode_canonical(test, truth)
+    log(f'[bench] workload: {n_queries} test x {n_truth} truth titles, vocab {len(enc["idf64"])}, '
+        f'mean trigrams/truth title {np.diff(enc["t_ptr"]).mean():.2f} ({time.time() - t0:.1f}s)')
+    return truth, test, enc
+
+
+def oracle_index(enc):
+    from oracle import oracle
+    return oracle.finish_index(dict(
+        n_truth=int(enc['t_ptr'].shape[0]) - 1, w64=enc['idf64'], w32=enc['idf64'].astype(np.float32), t_ptr=enc['t_ptr'],
+        t_cols=enc['t_cols'].astype(np.int32), q_ptr=enc['q_ptr'], q_cols=enc['q_cols'].astype(np.int32)))
+
+
+def cpu_sample(n_queries, size):
+    rng = np.random.default_rng(20240504)
+    return np.sort(rng.choice(n_queries, size=min(size, n_queries), replace=False))
+
+
+def time_cpu_port(index, sample, k):
+    """The CPU port of match_maker.py:192-203 (oracle/ds_oracle.c, OpenMP over queries) on `sample`."""
+    from oracle import oracle
+    t0 = time.perf_counter()
+    rows, count, _ = oracle.topn(index, k, queries=sample)
+    return time.perf_counter() - t0, rows, count
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits',
+                                          '-lms', '200', '-i', str(self.device)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, sm_max, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                sm_max.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, value in zip(names, parts[5:9]):
+                if value.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(sm_max) if sm_max else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def committed_traffic():
+    """DRAM bytes per k_scan launch from the committed ncu capture, if one has been summarised."""
+    path = os.path.join(ROOT, 'profiles', 'k_scan_traffic.json')
+    if os.path.exists(path):
+        return json.load(open(path)).get('dram_bytes_per_launch')
+    return None
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from oracle import oracle
+    truth, test, enc = build_workload(args.queries, args.truth)
+    index = oracle_index(enc)
+    sample = cpu_sample(args.queries, args.cpu_sample)
+    for _ in range(args.warmup):
+        time_cpu_port(index, sample[:max(8, len(sample) // 16)], args.top_n)
+    times = [time_cpu_port(index, sample, args.top_n)[0] for _ in range(args.steps)]
+    per_step = float(np.mean(times))
+    value = len(sample) / per_step
+    cores = oracle.max_threads()
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': per_step * 1e3, 'higher_is_better': True, 'scaling': 'strong',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args, enc),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': f'{len(sample)} sampled queries x all {args.truth} truth rows per step, '
+                                   f'top-{args.top_n}; titles/s = sample / time (linear in Q)'},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, enc):
+    return {'workload': f'C3 synthetic {args.queries} test x {args.truth} truth titles, nearest-n={args.top_n} '
+                        f'IDF-weighted trigram Jaccard top-n (BASELINE.json configs[2])',
+            'queries': args.queries, 'truth': args.truth, 'top_n': args.top_n, 'vocab': int(len(enc['idf64'])),
+            'mean_trigrams_per_truth_title': float(np.diff(enc['t_ptr']).mean()),
+            'l2': 'flushed between timed steps (256 MiB memset, untimed)',
+            'shard': 'truth rows, contiguous ranges, one per rank'}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from doppelspeller_b200 import _native as nat
+    from doppelspeller_b200 import sharded
+    from doppelspeller_b200.index import TruthIndex
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a GPU: doppelspeller_b200 has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+    k = args.top_n
+    truth, test, enc = build_workload(args.queries, args.truth)
+    n_q, n_truth = args.queries, args.truth
+    offs = sharded.shard_offsets(n_truth, world)
+    ptr, cols = sharded.slice_truth_csr(enc['t_ptr'], enc['t_cols'], int(offs[rank]), int(offs[rank + 1]))
+    t0 = time.time()
+    index = TruthIndex(ptr, cols, enc['idf64'], device=local_rank, row_offset=int(offs[rank]), n_total=n_truth)
+    torch.cuda.synchronize()
+    log(f'[bench] rank {rank}: index of rows [{offs[rank]}, {offs[rank + 1]}) built in {time.time() - t0:.2f}s')
+
+    d_q_ptr = torch.as_tensor(enc['q_ptr']).to(device)
+    d_q_cols = torch.as_tensor(enc['q_cols']).to(device)
+    h_q_ptr = torch.as_tensor(enc['q_ptr']).pin_memory()
+    h_q_cols = torch.as_tensor(enc['q_cols']).pin_memory()
+    h_rows = torch.empty((n_q, k), dtype=torch.int64).pin_memory()
+    h_count = torch.empty((n_q,), dtype=torch.int32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    shard = sharded.GpuShard(index, enc['q_ptr'], enc['q_cols']) if world > 1 else None
+
+    def step_device():
+        if world > 1:
+            rows, count, _ = sharded.sharded_topn(shard, k)
+            return rows, count
+        return index.topn(d_q_ptr, d_q_cols, k)
+
+    def step_e2e():
+        if world > 1:
+            sh = sharded.GpuShard(index, h_q_ptr.numpy(), h_q_cols.numpy())       # H2D of the queries
+            rows, count, _ = sharded.sharded_topn(sh, k)
+            h_rows.copy_(rows, non_blocking=True)                                 # D2H of the result
+            h_count.copy_(count, non_blocking=True)
+            torch.cuda.synchronize()
+            return h_rows, h_count
+        return index.topn(h_q_ptr, h_q_cols, k, out_rows=h_rows, out_count=h_count)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        total_ms = 0.0
+        result = None
+        for _ in range(steps):
+            flush.zero_()
+            barrier()
+            start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            start.record()
+            result = fn()
+            stop.record()
+            stop.synchronize()
+            total_ms += start.elapsed_time(stop)
+        barrier()
+        t = torch.tensor([total_ms], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), result
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches_before = nat.kernel_launches()
+    nat.profile_begin()
+    total_ms, (rows, count) = timed(step_device, args.steps)
+    scan_ms, scan_launches, scan_pairs = nat.profile_end()
+    gpu_launches = nat.kernel_launches() - launches_before
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    value = n_q / (ms_per_step / 1e3)
+
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    e2e_ms, (e_rows, e_count) = timed(step_e2e, args.steps)
+    e2e_value = n_q / (e2e_ms / args.steps / 1e3)
+    h2d = int(enc['q_ptr'].nbytes + enc['q_cols'].nbytes)
+    d2h = int(n_q * k * 8 + n_q * 4)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # roofline of the dominant kernel (k_scan): algorithmic bytes = (query, truth) pairs x (2 * g_truth + 8) B
+    peak, peak_source = measured_peak()
+    bytes_per_pair = 2.0 * float(np.diff(enc['t_ptr']).mean()) + 8.0
+    achieved = scan_pairs * bytes_per_pair / (scan_ms / 1e3) / 1e9 if scan_ms > 0 else 0.0
+    roofline = {'bound': 'hbm', 'kernel': 'k_scan', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': committed_traffic(), 'peak_source': peak_source, 'algorithmic_bytes_per_pair': bytes_per_pair,
+                'launches': int(scan_launches), 'avg_launch_ms': scan_ms / max(1, scan_launches),
+                'kernel_share_of_step': scan_ms / total_ms if total_ms > 0 else None,
+                'note': 'reporting convention of SURVEY.md 8(d): the truth index is L2 resident and reused by every '
+                        'query tile, so frac > 1 is expected; the kernel is issue bound (see profiles/)'}
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic', 'config': workload_config(args, enc), 'roofline': roofline,
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'ms_per_step': e2e_ms / args.steps},
+        'gpu_launches': int(gpu_launches), 'clocks': clocks,
+    }
+
+    rows_np = rows.cpu().numpy() if hasattr(rows, 'cpu') else rows
+    e_rows_np = e_rows.numpy() if hasattr(e_rows, 'numpy') else e_rows
+    line['parity'] = {'e2e_equals_device_path': bool(np.array_equal(rows_np, e_rows_np))}
+    if world == 1 and not args.no_cpu:
+        from oracle import oracle
+        index_cpu = oracle_index(enc)
+        sample = cpu_sample(n_q, args.cpu_sample)
+        time_cpu_port(index_cpu, sample[:64], k)
+        seconds, want_rows, want_count = time_cpu_port(index_cpu, sample, k)
+        line['cpu_baseline'] = {'value': len(sample) / seconds, 'unit': UNIT, 'cores': oracle.max_threads(), 'kind': 'port',
+                                'sample': f'{len(sample)} sampled queries x all {n_truth} truth rows, top-{k}, '
+                                          f'{seconds:.1f}s; titles/s = sample / time (linear in Q)'}
+        line['parity'].update({'checked_queries': int(len(sample)),
+                               'mismatching_queries': int((rows_np[sample] != want_rows).any(axis=1).sum())})
+        line['extra'] = pair_kernels(truth, test, rows_np, device)
+    if world > 1:
+        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+
+
+def pair_kernels(truth, test, rows, device):
+    """Secondary metrics (BASELINE.json: "Levenshtein pairs/sec"): K2 InDel ratio and K3 66-feature kernels on
+    the candidate pairs of the step (compact title tables resident in HBM)."""
+    import torch
+    from collections import Counter
+    from doppelspeller_b200 import _native as nat
+    from doppelspeller_b200 import feature_engineering as fe
+    n_q, k = rows.shape
+    codes_a, off_a = fe.encode_titles(test)
+    codes_b, off_b = fe.encode_titles(truth)
+    counter = Counter(w for t in truth for w in set(t.split()))
+    counts = np.zeros((len(truth), 15), dtype=np.uint32)
+    for i, t in enumerate(truth):
+        ws = [counter[w] for w in t.split()[:15]]
+        counts[i, :len(ws)] = ws
+    dev = lambda x: torch.as_tensor(x).to(device)   # noqa: E731
+    d = dict(a=dev(codes_a), oa=dev(off_a), b=dev(codes_b), ob=dev(off_b), c=dev(counts.view(np.int32)),
+             ia=dev(np.repeat(np.arange(n_q, dtype=np.int32), k)), ib=dev(rows.reshape(-1).astype(np.int32)))
+    n = n_q * k
+    ratio = torch.empty(n, dtype=torch.uint8, device=device)
+    feats = torch.empty((n, 66), dtype=torch.float32, device=device)
+
+    def run_ratio():
+        nat.check(nat.lib.ds_indel_ratio_pairs(nat.ptr(d['a']), nat.ptr(d['oa']), len(test), nat.ptr(d['b']), nat.ptr(d['ob']),
+                                               len(truth), nat.ptr(d['ia']), nat.ptr(d['ib']), n, nat.ptr(ratio), None,
+                                               nat.current_stream()))
+
+    def run_feats():
+        fe.construct_features_pairs((d['a'], d['oa']), (d['b'], d['ob']), d['c'], d['ia'], d['ib'], fe.SPACE_CODE, len(truth),
+                                    response=feats)
+
+    out = {}
+    la = np.diff(off_a)[np.repeat(np.arange(n_q), k)]
+    lb = np.diff(off_b)[rows.reshape(-1)]
+    for name, fn, bytes_per_pair in (('indel_ratio', run_ratio, float((la + lb).mean()) + 3.0),
+                                     ('construct_features', run_feats, float((la + lb).mean()) + 2.0 + 60.0 + 264.0)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(3):
+            fn()
+        stop.record()
+        stop.synchronize()
+        ms = start.elapsed_time(stop) / 3
+        peak, _ = measured_peak()
+        out[name] = {'pairs_per_s': n / (ms / 1e3), 'pairs': n, 'ms': ms, 'algorithmic_bytes_per_pair': bytes_per_pair,
+                     'hbm_frac': n * bytes_per_pair / (ms / 1e3) / 1e9 / peak}
+    return out
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--gpus', type=int, default=1)
+    parser.add_argument('--steps', type=int, default=3)
+    parser.add_argument('--warmup', type=int, default=3)
+    parser.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    parser.add_argument('--queries', type=int, default=100000)
+    parser.add_argument('--truth', type=int, default=500000)
+    parser.add_argument('--top-n', type=int, default=10)
+    parser.add_argument('--cpu-sample', type=int, default=2000)
+    parser.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline / parity sample (profiling runs)')
+    args = parser.parse_args()
+    import __graft_entry__ as entry
+    lib = os.path.join(ROOT, 'doppelspeller_b200', '_lib', 'libdoppelspeller_b200.so')
+    if not os.path.exists(lib) or not os.path.exists(os.path.join(ROOT, 'oracle', '_build', 'libds_oracle.so')):
+        entry.build()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

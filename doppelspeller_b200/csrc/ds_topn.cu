@@ -32,6 +32,14 @@ namespace ds {
 thread_local char g_last_error[512] = "";
 std::atomic<int64_t> g_kernel_launches{0};
 
+// optional timing of the dominant kernel (k_scan) for bench.py's roofline: CUDA events on the launching stream
+struct ScanProfile {
+    bool enabled = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+    double pairs = 0.0;
+};
+static ScanProfile g_profile;
+
 constexpr int TQ = 32;              // queries per tile (one bit each in the slot mask)
 constexpr int MAX_SLOTS = 2048;     // slot 0 = "column not in this tile"
 constexpr int CAND_CAP = 1024;      // per query candidate buffer (per scan launch)
@@ -696,7 +704,7 @@ static void plan_tiles(const QuerySet &qs, const std::vector<int32_t> &batch, st
     }
 }
 
-static int launch_scan(const Index &ix, cudaStream_t stream, ScanParams sp, int n_tiles) {
+static int launch_scan(const Index &ix, cudaStream_t stream, ScanParams sp, int n_tiles, int n_queries) {
     const size_t smem = scan_smem_bytes(ix.n_vocab);
     const int64_t rows = sp.r1 - sp.r0;
     if (rows <= 0 || n_tiles <= 0) return DS_OK;
@@ -712,6 +720,12 @@ static int launch_scan(const Index &ix, cudaStream_t stream, ScanParams sp, int 
         ScanParams part = sp;
         part.tile_q = sp.tile_q + (size_t)t0 * TQ;
         dim3 grid((unsigned)row_ctas, (unsigned)nt);
+        cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+        if (g_profile.enabled) {
+            DS_CUDA(cudaEventCreate(&ev_start));
+            DS_CUDA(cudaEventCreate(&ev_stop));
+            DS_CUDA(cudaEventRecord(ev_start, stream));
+        }
         if (big) {
             static bool attr_done = false;
             if (!attr_done) {
@@ -728,6 +742,11 @@ static int launch_scan(const Index &ix, cudaStream_t stream, ScanParams sp, int 
             k_scan<256><<<grid, 256, smem, stream>>>(part);
         }
         DS_LAUNCHED("k_scan");
+        if (g_profile.enabled) {
+            DS_CUDA(cudaEventRecord(ev_stop, stream));
+            g_profile.events.emplace_back(ev_start, ev_stop);
+            g_profile.pairs += (double)rows * (double)n_queries * ((double)nt / (double)n_tiles);
+        }
     }
     return DS_OK;
 }
@@ -832,7 +851,7 @@ static int run_local_batch(Workspace &call_ws, const Index &ix, const QuerySet &
         sp.r0 = (int)r0;
         sp.r1 = (int)r1;
         sp.dense = dense ? d_dense : nullptr;
-        DS_CHECK(launch_scan(ix, stream, sp, n_tiles));
+        DS_CHECK(launch_scan(ix, stream, sp, n_tiles, n_batch));
         sel.dense = dense ? d_dense : nullptr;
         sel.dense_rows = dense ? (int)(r1 - r0) : 0;
         sel.dense_r0 = (int)r0;
@@ -970,7 +989,7 @@ static int rescan_topn(Workspace &call_ws, const Index &ix, const QuerySet &qs, 
             int64_t r0 = std::max<int64_t>(0, r1 - FIXED_ROWS);
             sp.r0 = (int)r0;
             sp.r1 = (int)r1;
-            DS_CHECK(launch_scan(ix, stream, sp, n_tiles));
+            DS_CHECK(launch_scan(ix, stream, sp, n_tiles, n_batch));
             DS_CUDA(cudaMemsetAsync(d_unfinished, 0, 4, stream));
             cp.dense_rows = (int)(r1 - r0);
             cp.dense_r0 = (int)r0;
@@ -1009,6 +1028,35 @@ struct ds_index {
 extern "C" {
 
 int ds_version(void) { return DS_VERSION; }
+
+int ds_profile_begin(void) {
+    for (auto &e : g_profile.events) {
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+    }
+    g_profile.events.clear();
+    g_profile.pairs = 0.0;
+    g_profile.enabled = true;
+    return DS_OK;
+}
+
+int ds_profile_end(double *scan_ms, int64_t *scan_launches, double *scan_pairs) {
+    g_profile.enabled = false;
+    double total = 0.0;
+    for (auto &e : g_profile.events) {
+        float ms = 0.0f;
+        DS_CUDA(cudaEventSynchronize(e.second));
+        DS_CUDA(cudaEventElapsedTime(&ms, e.first, e.second));
+        total += ms;
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+    }
+    if (scan_ms) *scan_ms = total;
+    if (scan_launches) *scan_launches = (int64_t)g_profile.events.size();
+    if (scan_pairs) *scan_pairs = g_profile.pairs;
+    g_profile.events.clear();
+    return DS_OK;
+}
 const char *ds_last_error(void) { return g_last_error; }
 int64_t ds_kernel_launches(void) { return g_kernel_launches.load(); }
 

@@ -72,17 +72,23 @@ class TruthIndex:
         if q_mx is not None:
             nat.expect(q_mx, 'float64', 'q_mx')
 
-    def topn(self, q_row_ptr, q_col_ids, k, q_mx=None, mx_mode=nat.DS_MX_PY312_COMPENSATED, with_details=False):
+    def topn(self, q_row_ptr, q_col_ids, k, q_mx=None, mx_mode=nat.DS_MX_PY312_COMPENSATED, with_details=False,
+             out_rows=None, out_count=None):
         """`[get_closest_matches(q) for q in queries]` as truth ROW indexes (match_maker.py:192-203).
 
         Returns (rows int64[Q,k] descending row index, count int32[Q]) and, with_details, also
-        (kth_key float32[Q], flags int32[Q])."""
+        (kth_key float32[Q], flags int32[Q]).  `out_rows` / `out_count` may be preallocated buffers (e.g.
+        pinned host tensors) to receive the result."""
         self._check_queries(q_row_ptr, q_col_ids, q_mx)
         n_q = int(q_row_ptr.shape[0]) - 1
         cuda = _is_cuda_tensor(q_col_ids)
         dev = q_col_ids.device if cuda else None
-        rows = _empty((n_q, k), 'int64', cuda, dev)
-        count = _empty((n_q,), 'int32', cuda, dev)
+        rows = out_rows if out_rows is not None else _empty((n_q, k), 'int64', cuda, dev)
+        count = out_count if out_count is not None else _empty((n_q,), 'int32', cuda, dev)
+        nat.expect(rows, 'int64', 'out_rows')
+        nat.expect(count, 'int32', 'out_count')
+        if tuple(rows.shape) != (n_q, k) or tuple(count.shape) != (n_q,):
+            raise ValueError('out_rows / out_count have the wrong shape')
         kth = _empty((n_q,), 'float32', cuda, dev) if with_details else None
         flags = _empty((n_q,), 'int32', cuda, dev) if with_details else None
         nat.check(nat.lib.ds_topn(self._handle, n_q, nat.ptr(q_row_ptr), nat.ptr(q_col_ids), nat.ptr(q_mx), mx_mode, k,

@@ -56,6 +56,11 @@ int ds_version(void);
 const char *ds_last_error(void);
 /* number of CUDA kernels this library has launched in the calling process (bench.py gpu_launches) */
 int64_t ds_kernel_launches(void);
+/* Measurement hooks (bench.py roofline): between ds_profile_begin and ds_profile_end every launch of the
+ * dominant kernel (the K1 scan) is bracketed by CUDA events on its own stream.  ds_profile_end waits
+ * for them and returns the summed device time, the launch count and the (query, truth) pairs scanned. */
+int ds_profile_begin(void);
+int ds_profile_end(double *scan_ms, int64_t *scan_launches, double *scan_pairs);
 
 /* ---------------------------------------------------------------------------------------------------
  * ds_index_create  -  replaces the truth-side half of MatchMaker.__init__ (match_maker.py:97-109:
