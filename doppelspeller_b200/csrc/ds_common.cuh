@@ -63,7 +63,7 @@ inline bool is_device_pointer(const void *p) {
 // Stream-ordered device allocation released in the destructor (cudaFreeAsync on the same stream).
 class Workspace {
    public:
-    explicit Workspace(cudaStream_t stream) : stream_(stream) {}
+    explicit Workspace(cudaStream_t stream) : stream_(stream) { keep_pool_memory(); }
     ~Workspace() {
         for (void *p : blocks_) cudaFreeAsync(p, stream_);
     }
@@ -126,6 +126,20 @@ class Workspace {
     cudaStream_t stream() const { return stream_; }
 
    private:
+    // By default the stream-ordered pool hands freed memory back to the OS at every synchronisation, which
+    // would make each call re-map its whole workspace; keep it cached in the pool instead.
+    static void keep_pool_memory() {
+        static thread_local int done_for_device = -1;
+        int device = 0;
+        if (cudaGetDevice(&device) != cudaSuccess || device == done_for_device) return;
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t threshold = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+        }
+        done_for_device = device;
+    }
+
     struct Pending {
         void *host;
         void *device;

@@ -42,11 +42,14 @@ static ScanProfile g_profile;
 
 constexpr int TQ = 32;              // queries per tile (one bit each in the slot mask)
 constexpr int MAX_SLOTS = 2048;     // slot 0 = "column not in this tile"
-constexpr int CAND_CAP = 1024;      // per query candidate buffer (per scan launch)
+constexpr int CAND_CAP_MAX = 1024;  // per query candidate buffer (per scan launch): clamp(8 * k, 256, 1024)
 constexpr int DENSE_ROWS = 256;     // rows of the first (dense, threshold seeding) chunk
 constexpr int FIXED_ROWS = 1024;    // chunk rows of the bounded-memory fallback / rescan passes
 constexpr int QUERY_BATCH = 65536;  // queries per workspace batch
 constexpr int STATE_OVERFLOW = 1;
+constexpr int SORT_BLOCK = 4096;    // rows are length-sorted inside blocks of this many consecutive rows
+constexpr int MODE_SCORE = 0;       // retained list = best m by (score, row); drives the running threshold
+constexpr int MODE_ROW = 1;         // retained list = the k highest rows with s64 >= a fixed threshold (rescan)
 
 struct Index {
     int device = 0;
@@ -55,9 +58,14 @@ struct Index {
     int64_t row_offset = 0;
     int64_t n_total = 0;
     uint64_t n_chunks = 0;
+    // Rows are stored in a permuted order: inside every block of SORT_BLOCK consecutive rows they are sorted
+    // by their chunk count, so the 32 rows of a warp stream (nearly) the same number of chunks.  Everything
+    // indexed by "position" below uses that order; perm[position] is the shard-local original row.
+    int32_t *perm = nullptr;        // [n_truth] position -> original row
     uint4 *chunks = nullptr;        // [n_chunks] eight ascending u16 column ids, sentinel = n_vocab
-    uint32_t *chunk_ptr = nullptr;  // [n_truth + 1]
-    float *sums = nullptr;          // [n_truth] sums_matrix_truth
+    uint32_t *chunk_ptr = nullptr;  // [n_truth + 1] by position
+    float *sums_pos = nullptr;      // [n_truth] sums_matrix_truth by position
+    float *sums = nullptr;          // [n_truth] sums_matrix_truth by original row
     float *w32 = nullptr;           // [n_vocab + 1], w32[n_vocab] = 0 (sentinel)
     double *w64 = nullptr;          // [n_vocab]
 };
@@ -109,30 +117,36 @@ __global__ void k_weights(const double *__restrict__ w64, float *__restrict__ w3
 // one thread per row: chunk count and (optionally) sums_matrix_truth = sequential f32 sum in the
 // caller's column order (match_maker.py:172-174)
 __global__ void k_row_prepare(const int64_t *__restrict__ row_ptr, const uint16_t *__restrict__ cols,
-                              const float *__restrict__ w32, int n_vocab, int64_t n_rows, uint32_t *__restrict__ n_chunks,
-                              float *__restrict__ sums, int compute_sums) {
-    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_rows) return;
+                              const float *__restrict__ w32, int n_vocab, int64_t n_rows, const int32_t *__restrict__ perm,
+                              uint32_t *__restrict__ n_chunks, float *__restrict__ sums, float *__restrict__ sums_pos,
+                              int compute_sums) {
+    int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= n_rows) return;
+    const int64_t r = perm[pos];
     int64_t p0 = row_ptr[r], p1 = row_ptr[r + 1];
-    n_chunks[r] = (uint32_t)((p1 - p0 + 7) / 8);
+    n_chunks[pos] = (uint32_t)((p1 - p0 + 7) / 8);
+    float acc = 0.0f;
     if (compute_sums) {
-        float acc = 0.0f;
         for (int64_t p = p0; p < p1; ++p) acc = __fadd_rn(acc, w32[min((int)cols[p], n_vocab)]);
         sums[r] = acc;
+    } else {
+        acc = sums[r];
     }
+    sums_pos[pos] = acc;
 }
 
 // one warp per row: rank-sort the row's column ids ascending into its sentinel padded chunks
 __global__ void k_row_pack(const int64_t *__restrict__ row_ptr, const uint16_t *__restrict__ cols,
-                           const uint32_t *__restrict__ chunk_ptr, int64_t n_rows, uint16_t sentinel,
-                           uint16_t *__restrict__ out) {
-    int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+                           const uint32_t *__restrict__ chunk_ptr, int64_t n_rows, const int32_t *__restrict__ perm,
+                           uint16_t sentinel, uint16_t *__restrict__ out) {
+    int64_t pos = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
     int lane = threadIdx.x & 31;
-    if (r >= n_rows) return;
+    if (pos >= n_rows) return;
+    const int64_t r = perm[pos];
     int64_t p0 = row_ptr[r];
     int g = (int)(row_ptr[r + 1] - p0);
-    uint16_t *dst = out + (size_t)chunk_ptr[r] * 8;
-    int padded = (int)(chunk_ptr[r + 1] - chunk_ptr[r]) * 8;
+    uint16_t *dst = out + (size_t)chunk_ptr[pos] * 8;
+    int padded = (int)(chunk_ptr[pos + 1] - chunk_ptr[pos]) * 8;
     for (int i = lane; i < padded; i += 32) {
         if (i >= g) dst[i] = sentinel;
     }
@@ -201,7 +215,7 @@ __global__ void k_query_prepare(const int64_t *__restrict__ q_ptr, const uint16_
 struct ScanParams {
     const uint4 *chunks;
     const uint32_t *chunk_ptr;
-    const float *sums;
+    const float *sums;          // by position
     const float *w32;
     int n_vocab;
     const uint16_t *q_sorted;   // call-level CSR, ascending per query
@@ -210,7 +224,7 @@ struct ScanParams {
     const int32_t *tile_q;      // [n_tiles * TQ] batch-local query ids, -1 = empty slot
     const float2 *ab;           // [n_batch] filter constants
     int r0, r1, rows_per_cta;
-    uint2 *cand;                // [n_batch * cap] (local row, f32 bits of sc)
+    uint2 *cand;                // [n_batch * cap] (row position, f32 bits of sc)
     int *cand_count;            // [n_batch]
     int cap;
     float *dense;               // non-null: write every sc to dense[b * dense_stride + (row - r0)]
@@ -334,18 +348,21 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) k_scan(ScanParams p) {
 // refresh the threshold / filter constants.  One warp per batch query.
 // ---------------------------------------------------------------------------------------------------
 struct SelectParams {
+    int mode;                 // MODE_SCORE / MODE_ROW
     const int32_t *batch_q;
     const double *q_mx;
-    const float *sums;
+    const double *threshold;  // MODE_ROW: call-level fixed thresholds
+    const float *sums;        // by position
+    const int32_t *perm;      // position -> shard-local original row
     int n_batch;
-    int k, m;
+    int k, m;                 // m = retained list length (MODE_ROW: m == k)
     const uint2 *cand;
     int *cand_count;
     int cap;
     const float *dense;
     int dense_stride, dense_rows, dense_r0;
-    double *ret_score;  // [n_batch * m] descending
-    int32_t *ret_row;   // [n_batch * m] local rows
+    double *ret_score;  // [n_batch * m]
+    int32_t *ret_row;   // [n_batch * m] original rows
     int *ret_n;
     double *theta;      // [n_batch] current exact threshold (<= 0: none yet)
     float2 *ab;
@@ -364,25 +381,34 @@ __global__ void __launch_bounds__(128) k_select(SelectParams p) {
     __shared__ double s_kth[4];
 
     if (p.state[b] & STATE_OVERFLOW) return;
-    const double mx = p.q_mx[p.batch_q[b]];
-    const double theta = p.theta[b];
+    const bool by_row = p.mode == MODE_ROW;
+    const int64_t q = p.batch_q[b];
+    const double mx = p.q_mx[q];
+    const double theta = by_row ? p.threshold[q] : p.theta[b];
     int n = 0;
     if (p.dense != nullptr) {
         for (int i0 = 0; i0 < p.dense_rows; i0 += 32) {
             int i = i0 + lane;
-            float sc = (i < p.dense_rows) ? p.dense[(size_t)b * p.dense_stride + i] : 0.0f;
-            int row = p.dense_r0 + i;
+            bool pass = false;
             double s = 0.0;
-            bool pass = sc > 0.0f;
-            if (pass) {
-                s = exact_score(sc, p.sums[row], mx);
-                pass = s > 0.0 && s >= theta;
+            int pos = p.dense_r0 + i;
+            if (i < p.dense_rows) {
+                float sc = p.dense[(size_t)b * p.dense_stride + i];
+                if (by_row) {
+                    // every row is a candidate: zero scores qualify for thr <= 0 and 0/0 = NaN never does,
+                    // exactly like numpy's `array >= threshold` (match_maker.py:71)
+                    s = exact_score(sc, p.sums[pos], mx);
+                    pass = s >= theta;
+                } else if (sc > 0.0f) {
+                    s = exact_score(sc, p.sums[pos], mx);
+                    pass = s > 0.0 && s >= theta;
+                }
             }
             unsigned ballot = __ballot_sync(0xffffffffu, pass);
             if (pass) {
-                int pos = n + __popc(ballot & ((1u << lane) - 1));
-                s_score[pos] = s;
-                s_row[pos] = row;
+                int at = n + __popc(ballot & ((1u << lane) - 1));
+                s_score[at] = s;
+                s_row[at] = p.perm[pos];
             }
             n += __popc(ballot);
         }
@@ -405,15 +431,15 @@ __global__ void __launch_bounds__(128) k_select(SelectParams p) {
             int row = 0;
             if (i < cnt) {
                 uint2 c = p.cand[(size_t)b * p.cap + i];
-                row = (int)c.x;
-                s = exact_score(__uint_as_float(c.y), p.sums[row], mx);
+                s = exact_score(__uint_as_float(c.y), p.sums[c.x], mx);
+                row = p.perm[c.x];
                 pass = s > 0.0 && s >= theta;
             }
             unsigned ballot = __ballot_sync(0xffffffffu, pass);
             if (pass) {
-                int pos = n + __popc(ballot & ((1u << lane) - 1));
-                s_score[pos] = s;
-                s_row[pos] = row;
+                int at = n + __popc(ballot & ((1u << lane) - 1));
+                s_score[at] = s;
+                s_row[at] = row;
             }
             n += __popc(ballot);
         }
@@ -433,7 +459,11 @@ __global__ void __launch_bounds__(128) k_select(SelectParams p) {
         const double si = s_score[i];
         const int ri = s_row[i];
         int rank = 0;
-        for (int j = 0; j < total; ++j) rank += better(s_score[j], s_row[j], si, ri);
+        if (by_row) {
+            for (int j = 0; j < total; ++j) rank += s_row[j] > ri;
+        } else {
+            for (int j = 0; j < total; ++j) rank += better(s_score[j], s_row[j], si, ri);
+        }
         if (rank < p.m) {
             p.ret_score[(size_t)b * p.m + rank] = si;
             p.ret_row[(size_t)b * p.m + rank] = ri;
@@ -444,12 +474,43 @@ __global__ void __launch_bounds__(128) k_select(SelectParams p) {
     if (lane == 0) {
         p.ret_n[b] = min(total, p.m);
         if (p.dense == nullptr) p.cand_count[b] = 0;
-        if (total >= p.k) {
+        if (!by_row && total >= p.k) {
             double th = threshold_from_key(__double2float_rn(s_kth[warp]));
             p.theta[b] = th;
             p.ab[b] = filter_from_threshold(th, mx);
         }
     }
+}
+
+// MODE_ROW set-up: filter constants from the fixed thresholds; queries whose threshold is <= 0 (every
+// non-NaN row qualifies) cannot use the positive-score filter and are marked for the dense pass
+__global__ void k_rescan_init(const int32_t *__restrict__ batch_q, int n_batch, const double *__restrict__ threshold,
+                              const double *__restrict__ q_mx, float2 *__restrict__ ab, int *__restrict__ state,
+                              int *__restrict__ overflow_count) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_batch) return;
+    const int64_t q = batch_q[b];
+    const double thr = threshold[q];
+    if (thr > 0.0) {
+        ab[b] = filter_from_threshold(thr, q_mx[q]);
+        state[b] = 0;
+    } else {
+        ab[b] = make_float2(__int_as_float(0x7f800000), __int_as_float(0x7f800000));
+        state[b] = STATE_OVERFLOW;
+        atomicAdd(overflow_count, 1);
+    }
+}
+
+// MODE_ROW result: retained rows (descending) -> call-level out_rows / out_count as global rows
+__global__ void k_export_rows(const int32_t *__restrict__ batch_q, int n_batch, int k, const int32_t *__restrict__ ret_row,
+                              const int *__restrict__ ret_n, int64_t row_offset, int64_t *__restrict__ out_rows,
+                              int32_t *__restrict__ out_count) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n_batch * k) return;
+    int b = (int)(i / k), slot = (int)(i % k);
+    int64_t q = batch_q[b];
+    out_rows[q * k + slot] = slot < ret_n[b] ? (int64_t)ret_row[i] + row_offset : -1;
+    if (slot == 0) out_count[q] = ret_n[b];
 }
 
 // copy the retained lists to the phase-1 output layout: [n_q, m] score desc / global row, -1 padded
@@ -567,66 +628,6 @@ __global__ void __launch_bounds__(128) k_merge(MergeParams p) {
         if (p.out_flags) p.out_flags[q] = flags;
         if ((flags & DS_FLAG_RESCAN) && p.flagged_count) atomicAdd(p.flagged_count, 1);
     }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// rescan (phase 3): the k highest local rows with s64 >= thr, walking dense chunks from the top
-// ---------------------------------------------------------------------------------------------------
-struct CollectParams {
-    const int32_t *batch_q;
-    const double *q_mx;
-    const double *threshold;  // call-level
-    const float *sums;
-    int n_batch, k;
-    const float *dense;
-    int dense_stride, dense_rows, dense_r0;
-    int64_t row_offset;
-    int64_t *out_rows;   // call-level [n_q * k]
-    int32_t *out_count;  // call-level
-    int *unfinished;
-};
-
-__global__ void __launch_bounds__(128) k_collect(CollectParams p) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * 4 + warp;
-    if (b >= p.n_batch) return;
-    const int64_t q = p.batch_q[b];
-    int count = p.out_count[q];
-    if (count >= p.k) return;
-    const double mx = p.q_mx[q], thr = p.threshold[q];
-    for (int i0 = p.dense_rows - 1; i0 >= 0 && count < p.k; i0 -= 32) {
-        int i = i0 - lane;  // lane order = descending row
-        bool pass = false;
-        if (i >= 0) {
-            float sc = p.dense[(size_t)b * p.dense_stride + i];
-            double s = exact_score(sc, p.sums[p.dense_r0 + i], mx);
-            pass = s >= thr;  // NaN compares false, like numpy's `array >= threshold`
-        }
-        unsigned ballot = __ballot_sync(0xffffffffu, pass);
-        if (pass) {
-            int pos = count + __popc(ballot & ((1u << lane) - 1));
-            if (pos < p.k) p.out_rows[q * p.k + pos] = (int64_t)(p.dense_r0 + i) + p.row_offset;
-        }
-        count += __popc(ballot);
-    }
-    if (lane == 0) {
-        p.out_count[q] = min(count, p.k);
-        if (count < p.k) atomicAdd(p.unfinished, 1);
-    }
-}
-
-__global__ void k_fill_i32(int32_t *p, int64_t n, int32_t v) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
-}
-
-__global__ void k_rescan_reset(const int32_t *batch_q, int n_batch, int k, int64_t *out_rows, int32_t *out_count) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)n_batch * k) return;
-    int b = (int)(i / k), slot = (int)(i % k);
-    int64_t q = batch_q[b];
-    out_rows[q * k + slot] = -1;
-    if (slot == 0) out_count[q] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -766,11 +767,22 @@ static int launch_select(cudaStream_t stream, SelectParams sp) {
     return DS_OK;
 }
 
-// Runs the scan + select pipeline for one batch of queries (ids into the call's query set) and
-// exports its retained lists.  `fixed` = bounded-memory mode: dense chunks of FIXED_ROWS rows only.
-static int run_local_batch(Workspace &call_ws, const Index &ix, const QuerySet &qs, const std::vector<int32_t> &batch,
-                           int k, int m, bool fixed, double *d_out_score, int64_t *d_out_row,
-                           std::vector<int32_t> *overflowed) {
+// Runs the scan + select pipeline for one batch of queries (ids into the call's query set).
+//   MODE_SCORE  phase 1: retained list = best m by score, exported as (score64, global row)
+//   MODE_ROW    phase 3: retained list = the k highest rows reaching the fixed threshold, exported as rows
+// `fixed` = bounded-memory form: dense chunks of FIXED_ROWS rows only (cannot overflow).  Otherwise the
+// first chunk (MODE_SCORE) is dense to seed the thresholds and the rest goes through the candidate
+// buffers; queries whose buffer overflows are returned in `overflowed` to be redone with `fixed`.
+struct PipelineOut {
+    double *score = nullptr;      // MODE_SCORE [n_q * m]
+    int64_t *row = nullptr;       // MODE_SCORE [n_q * m]
+    int64_t *rows_k = nullptr;    // MODE_ROW   [n_q * k]
+    int32_t *count = nullptr;     // MODE_ROW   [n_q]
+};
+
+static int run_pipeline(Workspace &call_ws, const Index &ix, const QuerySet &qs, const std::vector<int32_t> &batch, int mode,
+                        int k, int m, bool fixed, const double *d_threshold, const PipelineOut &out,
+                        std::vector<int32_t> *overflowed) {
     cudaStream_t stream = call_ws.stream();
     const int n_batch = (int)batch.size();
     if (n_batch == 0) return DS_OK;
@@ -785,6 +797,8 @@ static int run_local_batch(Workspace &call_ws, const Index &ix, const QuerySet &
     uint2 *d_cand = nullptr;
     double *d_ret_score = nullptr, *d_theta = nullptr;
     float *d_dense = nullptr;
+    const int cand_cap = mode == MODE_ROW ? CAND_CAP_MAX : std::min(CAND_CAP_MAX, std::max(256, 8 * k));
+    const bool dense_first = mode == MODE_SCORE;
     const int dense_rows = fixed ? FIXED_ROWS : std::max(DENSE_ROWS, ((2 * k + 255) / 256) * 256);
     DS_CHECK(ws.alloc(&d_batch, n_batch));
     DS_CHECK(ws.alloc(&d_tile, tile_q.size()));
@@ -796,8 +810,8 @@ static int run_local_batch(Workspace &call_ws, const Index &ix, const QuerySet &
     DS_CHECK(ws.alloc(&d_overflow, 1));
     DS_CHECK(ws.alloc(&d_ab, n_batch));
     DS_CHECK(ws.alloc(&d_theta, n_batch));
-    DS_CHECK(ws.alloc(&d_dense, (size_t)n_batch * dense_rows));
-    if (!fixed) DS_CHECK(ws.alloc(&d_cand, (size_t)n_batch * CAND_CAP));
+    if (fixed || dense_first) DS_CHECK(ws.alloc(&d_dense, (size_t)n_batch * dense_rows));
+    if (!fixed) DS_CHECK(ws.alloc(&d_cand, (size_t)n_batch * cand_cap));
     DS_CUDA(cudaMemcpyAsync(d_batch, batch.data(), (size_t)n_batch * 4, cudaMemcpyHostToDevice, stream));
     DS_CUDA(cudaMemcpyAsync(d_tile, tile_q.data(), tile_q.size() * 4, cudaMemcpyHostToDevice, stream));
     DS_CUDA(cudaMemsetAsync(d_cand_count, 0, (size_t)n_batch * 4, stream));
@@ -806,11 +820,16 @@ static int run_local_batch(Workspace &call_ws, const Index &ix, const QuerySet &
     DS_CUDA(cudaMemsetAsync(d_overflow, 0, 4, stream));
     DS_CUDA(cudaMemsetAsync(d_ab, 0, (size_t)n_batch * 8, stream));
     DS_CUDA(cudaMemsetAsync(d_theta, 0, (size_t)n_batch * 8, stream));
+    if (mode == MODE_ROW && !fixed) {
+        k_rescan_init<<<(unsigned)ceil_div(n_batch, 256), 256, 0, stream>>>(d_batch, n_batch, d_threshold, qs.d_mx, d_ab, d_state,
+                                                                             d_overflow);
+        DS_LAUNCHED("k_rescan_init");
+    }
 
     ScanParams sp{};
     sp.chunks = ix.chunks;
     sp.chunk_ptr = ix.chunk_ptr;
-    sp.sums = ix.sums;
+    sp.sums = ix.sums_pos;
     sp.w32 = ix.w32;
     sp.n_vocab = ix.n_vocab;
     sp.q_sorted = qs.d_sorted;
@@ -820,19 +839,22 @@ static int run_local_batch(Workspace &call_ws, const Index &ix, const QuerySet &
     sp.ab = d_ab;
     sp.cand = d_cand;
     sp.cand_count = d_cand_count;
-    sp.cap = CAND_CAP;
+    sp.cap = cand_cap;
     sp.dense_stride = dense_rows;
 
     SelectParams sel{};
+    sel.mode = mode;
     sel.batch_q = d_batch;
     sel.q_mx = qs.d_mx;
-    sel.sums = ix.sums;
+    sel.threshold = d_threshold;
+    sel.sums = ix.sums_pos;
+    sel.perm = ix.perm;
     sel.n_batch = n_batch;
     sel.k = k;
     sel.m = m;
     sel.cand = d_cand;
     sel.cand_count = d_cand_count;
-    sel.cap = fixed ? 0 : CAND_CAP;
+    sel.cap = fixed ? 0 : cand_cap;
     sel.dense_stride = dense_rows;
     sel.ret_score = d_ret_score;
     sel.ret_row = d_ret_row;
@@ -846,8 +868,11 @@ static int run_local_batch(Workspace &call_ws, const Index &ix, const QuerySet &
     int64_t r0 = 0;
     bool first = true;
     while (r0 < n) {
-        const bool dense = fixed || first;
-        int64_t r1 = dense ? std::min<int64_t>(n, r0 + dense_rows) : std::min<int64_t>(n, std::max<int64_t>(2 * r0, r0 + dense_rows));
+        const bool dense = fixed || (first && dense_first);
+        int64_t r1;
+        if (dense) r1 = std::min<int64_t>(n, r0 + dense_rows);
+        else if (mode == MODE_ROW) r1 = n;  // the threshold is fixed: one pass over all rows
+        else r1 = std::min<int64_t>(n, std::max<int64_t>(2 * r0, r0 + dense_rows));
         sp.r0 = (int)r0;
         sp.r1 = (int)r1;
         sp.dense = dense ? d_dense : nullptr;
@@ -859,9 +884,15 @@ static int run_local_batch(Workspace &call_ws, const Index &ix, const QuerySet &
         r0 = r1;
         first = false;
     }
-    k_export<<<(unsigned)ceil_div((int64_t)n_batch * m, 256), 256, 0, stream>>>(d_batch, n_batch, m, d_ret_score, d_ret_row,
-                                                                                d_ret_n, ix.row_offset, d_out_score, d_out_row);
-    DS_LAUNCHED("k_export");
+    if (mode == MODE_SCORE) {
+        k_export<<<(unsigned)ceil_div((int64_t)n_batch * m, 256), 256, 0, stream>>>(d_batch, n_batch, m, d_ret_score, d_ret_row,
+                                                                                    d_ret_n, ix.row_offset, out.score, out.row);
+        DS_LAUNCHED("k_export");
+    } else {
+        k_export_rows<<<(unsigned)ceil_div((int64_t)n_batch * k, 256), 256, 0, stream>>>(d_batch, n_batch, k, d_ret_row, d_ret_n,
+                                                                                         ix.row_offset, out.rows_k, out.count);
+        DS_LAUNCHED("k_export_rows");
+    }
     if (!fixed && overflowed != nullptr) {
         int h_overflow = 0;
         DS_CUDA(cudaMemcpyAsync(&h_overflow, d_overflow, 4, cudaMemcpyDeviceToHost, stream));
@@ -877,23 +908,32 @@ static int run_local_batch(Workspace &call_ws, const Index &ix, const QuerySet &
     return DS_OK;
 }
 
-static int local_topn(Workspace &ws, const Index &ix, const QuerySet &qs, int k, int m, double *d_out_score,
-                      int64_t *d_out_row) {
+// runs `ids` through the pipeline in workspace-sized batches, then redoes the overflowed ones in the
+// bounded-memory form (adversarial row order, massive ties, thresholds <= 0)
+static int run_batches(Workspace &ws, const Index &ix, const QuerySet &qs, const std::vector<int32_t> &ids, int mode, int k, int m,
+                       const double *d_threshold, const PipelineOut &out) {
     std::vector<int32_t> overflowed;
-    for (int64_t q0 = 0; q0 < qs.n_q; q0 += QUERY_BATCH) {
-        int64_t q1 = std::min<int64_t>(qs.n_q, q0 + QUERY_BATCH);
-        std::vector<int32_t> batch((size_t)(q1 - q0));
-        for (int64_t q = q0; q < q1; ++q) batch[(size_t)(q - q0)] = (int32_t)q;
-        DS_CHECK(run_local_batch(ws, ix, qs, batch, k, m, false, d_out_score, d_out_row, &overflowed));
+    for (size_t i0 = 0; i0 < ids.size(); i0 += QUERY_BATCH) {
+        size_t i1 = std::min(ids.size(), i0 + QUERY_BATCH);
+        std::vector<int32_t> batch(ids.begin() + i0, ids.begin() + i1);
+        DS_CHECK(run_pipeline(ws, ix, qs, batch, mode, k, m, false, d_threshold, out, &overflowed));
     }
-    // queries whose candidate buffer overflowed (adversarial row order / massive ties) are redone in the
-    // bounded-memory mode, which cannot overflow
-    for (size_t i = 0; i < overflowed.size(); i += QUERY_BATCH / 8) {
-        size_t j = std::min(overflowed.size(), i + QUERY_BATCH / 8);
-        std::vector<int32_t> batch(overflowed.begin() + i, overflowed.begin() + j);
-        DS_CHECK(run_local_batch(ws, ix, qs, batch, k, m, true, d_out_score, d_out_row, nullptr));
+    for (size_t i0 = 0; i0 < overflowed.size(); i0 += QUERY_BATCH / 8) {
+        size_t i1 = std::min(overflowed.size(), i0 + QUERY_BATCH / 8);
+        std::vector<int32_t> batch(overflowed.begin() + i0, overflowed.begin() + i1);
+        DS_CHECK(run_pipeline(ws, ix, qs, batch, mode, k, m, true, d_threshold, out, nullptr));
     }
     return DS_OK;
+}
+
+static int local_topn(Workspace &ws, const Index &ix, const QuerySet &qs, int k, int m, double *d_out_score,
+                      int64_t *d_out_row) {
+    std::vector<int32_t> ids((size_t)qs.n_q);
+    for (int64_t q = 0; q < qs.n_q; ++q) ids[(size_t)q] = (int32_t)q;
+    PipelineOut out;
+    out.score = d_out_score;
+    out.row = d_out_row;
+    return run_batches(ws, ix, qs, ids, MODE_SCORE, k, m, nullptr, out);
 }
 
 static int merge_topn(cudaStream_t stream, int n_shards, int64_t n_q, int k, int m, int64_t n_total, const double *d_score,
@@ -929,82 +969,14 @@ static int merge_topn(cudaStream_t stream, int n_shards, int64_t n_q, int k, int
     return DS_OK;
 }
 
-// exact re-scan of the local shard for `flagged` queries with known thresholds (> 0 or the NaN edge)
-static int rescan_topn(Workspace &call_ws, const Index &ix, const QuerySet &qs, const double *d_threshold,
+// exact re-scan of the local shard for `flagged` queries with known thresholds: the k highest local rows
+// whose float64 score reaches the threshold (phase 3)
+static int rescan_topn(Workspace &ws, const Index &ix, const QuerySet &qs, const double *d_threshold,
                        const std::vector<int32_t> &flagged, int k, int64_t *d_out_rows, int32_t *d_out_count) {
-    cudaStream_t stream = call_ws.stream();
-    for (size_t i0 = 0; i0 < flagged.size(); i0 += QUERY_BATCH / 8) {
-        size_t i1 = std::min(flagged.size(), i0 + QUERY_BATCH / 8);
-        std::vector<int32_t> batch(flagged.begin() + i0, flagged.begin() + i1);
-        const int n_batch = (int)batch.size();
-        Workspace ws(stream);
-        std::vector<int32_t> tile_q;
-        plan_tiles(qs, batch, &tile_q);
-        const int n_tiles = (int)(tile_q.size() / TQ);
-        int32_t *d_batch = nullptr, *d_tile = nullptr;
-        float *d_dense = nullptr;
-        int *d_unfinished = nullptr;
-        float2 *d_ab = nullptr;
-        DS_CHECK(ws.alloc(&d_batch, n_batch));
-        DS_CHECK(ws.alloc(&d_tile, tile_q.size()));
-        DS_CHECK(ws.alloc(&d_dense, (size_t)n_batch * FIXED_ROWS));
-        DS_CHECK(ws.alloc(&d_unfinished, 1));
-        DS_CHECK(ws.alloc(&d_ab, n_batch));
-        DS_CUDA(cudaMemcpyAsync(d_batch, batch.data(), (size_t)n_batch * 4, cudaMemcpyHostToDevice, stream));
-        DS_CUDA(cudaMemcpyAsync(d_tile, tile_q.data(), tile_q.size() * 4, cudaMemcpyHostToDevice, stream));
-        DS_CUDA(cudaMemsetAsync(d_ab, 0, (size_t)n_batch * 8, stream));
-        k_rescan_reset<<<(unsigned)ceil_div((int64_t)n_batch * k, 256), 256, 0, stream>>>(d_batch, n_batch, k, d_out_rows, d_out_count);
-        DS_LAUNCHED("k_rescan_reset");
-
-        ScanParams sp{};
-        sp.chunks = ix.chunks;
-        sp.chunk_ptr = ix.chunk_ptr;
-        sp.sums = ix.sums;
-        sp.w32 = ix.w32;
-        sp.n_vocab = ix.n_vocab;
-        sp.q_sorted = qs.d_sorted;
-        sp.q_ptr = qs.d_ptr;
-        sp.batch_q = d_batch;
-        sp.tile_q = d_tile;
-        sp.ab = d_ab;
-        sp.dense = d_dense;
-        sp.dense_stride = FIXED_ROWS;
-        CollectParams cp{};
-        cp.batch_q = d_batch;
-        cp.q_mx = qs.d_mx;
-        cp.threshold = d_threshold;
-        cp.sums = ix.sums;
-        cp.n_batch = n_batch;
-        cp.k = k;
-        cp.dense = d_dense;
-        cp.dense_stride = FIXED_ROWS;
-        cp.row_offset = ix.row_offset;
-        cp.out_rows = d_out_rows;
-        cp.out_count = d_out_count;
-        cp.unfinished = d_unfinished;
-
-        int64_t r1 = ix.n_truth;
-        int iteration = 0;
-        while (r1 > 0) {
-            int64_t r0 = std::max<int64_t>(0, r1 - FIXED_ROWS);
-            sp.r0 = (int)r0;
-            sp.r1 = (int)r1;
-            DS_CHECK(launch_scan(ix, stream, sp, n_tiles, n_batch));
-            DS_CUDA(cudaMemsetAsync(d_unfinished, 0, 4, stream));
-            cp.dense_rows = (int)(r1 - r0);
-            cp.dense_r0 = (int)r0;
-            k_collect<<<(unsigned)ceil_div(n_batch, 4), 128, 0, stream>>>(cp);
-            DS_LAUNCHED("k_collect");
-            r1 = r0;
-            if ((++iteration % 4) == 0 && r1 > 0) {
-                int h_unfinished = 0;
-                DS_CUDA(cudaMemcpyAsync(&h_unfinished, d_unfinished, 4, cudaMemcpyDeviceToHost, stream));
-                DS_CUDA(cudaStreamSynchronize(stream));
-                if (h_unfinished == 0) break;
-            }
-        }
-    }
-    return DS_OK;
+    PipelineOut out;
+    out.rows_k = d_out_rows;
+    out.count = d_out_count;
+    return run_batches(ws, ix, qs, flagged, MODE_ROW, k, k, d_threshold, out);
 }
 
 static int check_topn_args(const Index *ix, int64_t n_q, const int64_t *q_row_ptr, const uint16_t *q_col_ids, int32_t k) {
@@ -1083,14 +1055,36 @@ int ds_index_create(ds_index **out, int device, int64_t n_truth, int32_t n_vocab
     DeviceGuard guard(device);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
 
-    int64_t nnz = 0;
+    std::vector<int64_t> h_ptr((size_t)n_truth + 1);
     if (is_device_pointer(t_row_ptr)) {
-        DS_CUDA(cudaMemcpyAsync(&nnz, t_row_ptr + n_truth, 8, cudaMemcpyDeviceToHost, stream));
+        DS_CUDA(cudaMemcpyAsync(h_ptr.data(), t_row_ptr, ((size_t)n_truth + 1) * 8, cudaMemcpyDeviceToHost, stream));
         DS_CUDA(cudaStreamSynchronize(stream));
     } else {
-        nnz = t_row_ptr[n_truth];
+        memcpy(h_ptr.data(), t_row_ptr, ((size_t)n_truth + 1) * 8);
     }
-    if (nnz < 0) return fail(DS_ERR_BAD_ARG, "t_row_ptr[n_truth] < 0");
+    const int64_t nnz = h_ptr[(size_t)n_truth];
+    if (h_ptr[0] != 0 || nnz < 0) return fail(DS_ERR_BAD_ARG, "t_row_ptr must start at 0 and be non-decreasing");
+    // position -> original row: stable counting sort by chunk count inside blocks of SORT_BLOCK rows
+    std::vector<int32_t> h_perm((size_t)n_truth);
+    {
+        std::vector<int32_t> bucket_start;
+        for (int64_t b0 = 0; b0 < n_truth; b0 += SORT_BLOCK) {
+            const int64_t b1 = std::min<int64_t>(n_truth, b0 + SORT_BLOCK);
+            int64_t max_chunks = 0;
+            for (int64_t r = b0; r < b1; ++r) {
+                const int64_t g = h_ptr[(size_t)r + 1] - h_ptr[(size_t)r];
+                if (g < 0) return fail(DS_ERR_BAD_ARG, "t_row_ptr is decreasing at row %lld", (long long)r);
+                max_chunks = std::max(max_chunks, (g + 7) / 8);
+            }
+            bucket_start.assign((size_t)max_chunks + 2, 0);
+            for (int64_t r = b0; r < b1; ++r) bucket_start[(size_t)((h_ptr[(size_t)r + 1] - h_ptr[(size_t)r] + 7) / 8) + 1]++;
+            for (size_t c = 1; c < bucket_start.size(); ++c) bucket_start[c] += bucket_start[c - 1];
+            for (int64_t r = b0; r < b1; ++r) {
+                const size_t c = (size_t)((h_ptr[(size_t)r + 1] - h_ptr[(size_t)r] + 7) / 8);
+                h_perm[(size_t)(b0 + bucket_start[c]++)] = (int32_t)r;
+            }
+        }
+    }
     if (nnz > 0 && t_col_ids == nullptr) return fail(DS_ERR_BAD_ARG, "t_col_ids is NULL");
 
     ds_index *handle = new (std::nothrow) ds_index();
@@ -1114,6 +1108,9 @@ int ds_index_create(ds_index **out, int device, int64_t n_truth, int32_t n_vocab
         DS_CUDA(cudaMalloc(&ix.w64, (size_t)n_vocab * 8));
         DS_CUDA(cudaMalloc(&ix.w32, ((size_t)n_vocab + 1) * 4));
         DS_CUDA(cudaMalloc(&ix.sums, (size_t)std::max<int64_t>(1, n_truth) * 4));
+        DS_CUDA(cudaMalloc(&ix.sums_pos, (size_t)std::max<int64_t>(1, n_truth) * 4));
+        DS_CUDA(cudaMalloc(&ix.perm, (size_t)std::max<int64_t>(1, n_truth) * 4));
+        DS_CUDA(cudaMemcpyAsync(ix.perm, h_perm.data(), (size_t)n_truth * 4, cudaMemcpyHostToDevice, stream));
         DS_CUDA(cudaMalloc(&ix.chunk_ptr, ((size_t)n_truth + 1) * 4));
         DS_CUDA(cudaMemcpyAsync(ix.w64, d_w64_in, (size_t)n_vocab * 8, cudaMemcpyDeviceToDevice, stream));
         k_weights<<<(unsigned)ceil_div(n_vocab + 1, 256), 256, 0, stream>>>(ix.w64, ix.w32, n_vocab);
@@ -1124,8 +1121,8 @@ int ds_index_create(ds_index **out, int device, int64_t n_truth, int32_t n_vocab
         if (n_truth > 0) {
             if (d_sums_in != nullptr)
                 DS_CUDA(cudaMemcpyAsync(ix.sums, d_sums_in, (size_t)n_truth * 4, cudaMemcpyDeviceToDevice, stream));
-            k_row_prepare<<<(unsigned)ceil_div(n_truth, 256), 256, 0, stream>>>(d_ptr, d_cols, ix.w32, n_vocab, n_truth, d_counts, ix.sums,
-                                                                               d_sums_in == nullptr ? 1 : 0);
+            k_row_prepare<<<(unsigned)ceil_div(n_truth, 256), 256, 0, stream>>>(d_ptr, d_cols, ix.w32, n_vocab, n_truth, ix.perm, d_counts,
+                                                                               ix.sums, ix.sums_pos, d_sums_in == nullptr ? 1 : 0);
             DS_LAUNCHED("k_row_prepare");
         }
         size_t temp_bytes = 0;
@@ -1141,8 +1138,8 @@ int ds_index_create(ds_index **out, int device, int64_t n_truth, int32_t n_vocab
         ix.n_chunks = total_chunks;
         DS_CUDA(cudaMalloc(&ix.chunks, std::max<size_t>(1, (size_t)total_chunks) * 16));
         if (n_truth > 0) {
-            k_row_pack<<<(unsigned)ceil_div(n_truth * 32, 256), 256, 0, stream>>>(d_ptr, d_cols, ix.chunk_ptr, n_truth, (uint16_t)n_vocab,
-                                                                                 reinterpret_cast<uint16_t *>(ix.chunks));
+            k_row_pack<<<(unsigned)ceil_div(n_truth * 32, 256), 256, 0, stream>>>(d_ptr, d_cols, ix.chunk_ptr, n_truth, ix.perm,
+                                                                                 (uint16_t)n_vocab, reinterpret_cast<uint16_t *>(ix.chunks));
             DS_LAUNCHED("k_row_pack");
         }
         DS_CUDA(cudaStreamSynchronize(stream));
@@ -1162,6 +1159,8 @@ int ds_index_destroy(ds_index *index) {
     cudaFree(index->ix.chunks);
     cudaFree(index->ix.chunk_ptr);
     cudaFree(index->ix.sums);
+    cudaFree(index->ix.sums_pos);
+    cudaFree(index->ix.perm);
     cudaFree(index->ix.w32);
     cudaFree(index->ix.w64);
     delete index;
