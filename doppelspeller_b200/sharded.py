@@ -82,9 +82,14 @@ def _all_gather(tensor, group, world):
     import torch.distributed as dist
     if world == 1:
         return tensor.unsqueeze(0)
-    out = torch.empty((world,) + tuple(tensor.shape), dtype=tensor.dtype, device=tensor.device)
-    dist.all_gather_into_tensor(out, tensor.contiguous(), group=group)
-    return out
+    tensor = tensor.contiguous()
+    if tensor.dim() == 0 or tensor.shape[0] == 0:
+        parts = [torch.empty_like(tensor) for _ in range(world)]
+        dist.all_gather(parts, tensor, group=group)
+        return torch.stack(parts)
+    flat = torch.empty((world * tensor.shape[0],) + tuple(tensor.shape[1:]), dtype=tensor.dtype, device=tensor.device)
+    dist.all_gather_into_tensor(flat, tensor, group=group)       # concatenated along dim 0 (NCCL and gloo)
+    return flat.view((world,) + tuple(tensor.shape))
 
 
 def sharded_topn(shard, k, group=None):

@@ -1,0 +1,121 @@
+"""CPU, build container only: the oracle restatement against the UNMODIFIED reference imported from
+/root/reference (numba kernels executed here).  Skipped where the reference is absent (GPU box) - there
+the golden vectors minted from these same functions pin the oracle (test_oracle_golden.py)."""
+import numpy as np
+import pytest
+
+from oracle import oracle, ref_import
+
+pytestmark = pytest.mark.skipif(not ref_import.reference_available(), reason='/root/reference is not present')
+
+N_QUERIES = 200
+
+
+@pytest.fixture(scope='module')
+def ref():
+    return ref_import.import_reference()
+
+
+@pytest.fixture(scope='module')
+def example(ref):
+    c = ref.constants
+    truth = ref.common.get_ground_truth()
+    test = ref.common.get_test_data().iloc[:N_QUERIES].copy()
+    mm = ref.match_maker.MatchMaker(test.copy(), truth.copy(), 100)
+    enc = oracle.encode_reference_order(list(test[c.COLUMN_N_GRAMS]), list(truth[c.COLUMN_N_GRAMS]))
+    return dict(truth=truth, test=test, mm=mm, index=oracle.finish_index(enc), enc=enc)
+
+
+def test_index_quantities(example):
+    mm, index, enc = example['mm'], example['index'], example['enc']
+    assert [mm.n_grams_decoding[i] for i in range(len(enc['vocab']))] == enc['vocab']          # match_maker.py:144-147
+    assert np.array_equal(mm.sums_matrix_truth.view(np.uint32), index['sums'].view(np.uint32))  # :172-174
+    for q in range(N_QUERIES):
+        assert np.array_equal(mm.matrix_non_zero_columns[q], index['qs_cols'][index['qs_ptr'][q]:index['qs_ptr'][q + 1]])
+    for v in range(0, len(enc['vocab']), 7):
+        rows = mm.matrix_truth_non_zero_columns_and_values[v][0]
+        assert np.array_equal(rows, index['post_rows'][index['post_ptr'][v]:index['post_ptr'][v + 1]])
+
+
+def test_python_sum_restatement(example):
+    mm, index = example['mm'], example['index']
+    for q in range(N_QUERIES):
+        nz = mm.matrix_non_zero_columns[q]
+        want = sum([mm._get_idf_given_index(r) for r in nz])                                   # match_maker.py:197
+        assert oracle.py_float_sum(index['w64'], nz) == want
+
+
+def test_fast_jaccard_bits(ref, example):
+    mm, index = example['mm'], example['index']
+    for q in range(0, N_QUERIES, 20):
+        nz = mm.matrix_non_zero_columns[q]
+        mx = sum([mm._get_idf_given_index(r) for r in nz])
+        want = ref.match_maker.fast_jaccard(mm.number_of_truth_titles, mx, nz, mm.matrix_truth_non_zero_columns_and_values,
+                                            mm.sums_matrix_truth)
+        got = oracle.fast_jaccard(index, q)
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+
+
+@pytest.mark.parametrize('k', [10, 100])
+def test_candidate_lists(ref, example, k):
+    mm, index, truth = example['mm'], example['index'], example['truth']
+    title_ids = truth[ref.constants.COLUMN_TITLE_ID].to_numpy()
+    rows, count, _ = oracle.topn(index, k)
+    mm.top_n = k
+    for q in range(N_QUERIES):
+        assert mm.get_closest_matches(q) == title_ids[rows[q]].tolist()
+
+
+def test_fast_arg_top_k_random(ref):
+    rng = np.random.default_rng(0)
+    fatk = ref.match_maker.fast_arg_top_k
+    for trial in range(200):
+        n, k = int(rng.integers(1, 400)), int(rng.integers(1, 50))
+        v = rng.random(n)
+        if trial % 3 == 0:
+            v = np.round(v, 1)
+        if trial % 5 == 0:
+            v[rng.random(n) < 0.8] = 0.0
+        if trial % 7 == 0:
+            v = 0.25 + rng.integers(-4, 5, n) * 3e-7
+        assert np.array_equal(oracle.fast_arg_top_k(v, k), fatk(v, k))
+
+
+def test_fast_levenshtein_ratio_random(ref):
+    rng = np.random.default_rng(1)
+    flr = ref.feature_engineering.fast_levenshtein_ratio
+    for trial in range(3000):
+        big = trial % 5 == 0
+        la, lb = int(rng.integers(1, 256 if big else 40)), int(rng.integers(1, 256 if big else 40))
+        alpha = int(rng.integers(2, 8))
+        a = rng.integers(1, 1 + alpha, la).astype(np.uint8)
+        b = rng.integers(1, 1 + alpha, lb).astype(np.uint8)
+        assert oracle.indel_ratio_u8(a, b) == int(flr(a, b))
+
+
+def test_construct_features_random(ref, example):
+    rng = np.random.default_rng(2)
+    c = ref.constants
+    truth_titles = list(example['truth'][c.COLUMN_TRANSFORMED_TITLE])
+    test_titles = list(example['test'][c.COLUMN_TRANSFORMED_TITLE])
+    pairs = [(test_titles[i % N_QUERIES], truth_titles[int(rng.integers(0, len(truth_titles)))]) for i in range(600)]
+    words = ['ab', 'cde', 'fghi', 'jk', 'lmnop', 'q', 'rst', 'uv', 'wxyz', 'a1', 'b22', 'c333', 'dd', 'ee', 'ffg', 'hh']
+    pairs += [(' '.join(rng.choice(words, max(1, n - 1))), ' '.join(rng.choice(words, n))) for n in range(1, 21) for _ in range(5)]
+    la = np.array([len(a) for a, b in pairs], np.uint8)
+    lb = np.array([len(b) for a, b in pairs], np.uint8)
+    ta = np.vstack([oracle.encode_title(a) for a, b in pairs])
+    tb = np.vstack([oracle.encode_title(b) for a, b in pairs])
+    counts = rng.integers(0, 3000, (len(pairs), 15)).astype(np.uint32)
+    want = np.zeros((len(pairs), 66), np.float32)
+    with np.errstate(all='ignore'):
+        ref.feature_engineering.construct_features(la, lb, ta, tb, counts, np.uint8(1), np.uint32(30000),
+                                                   np.zeros(66, np.uint8), want)
+    got = oracle.construct_features(la, lb, ta, tb, counts, 1, 30000)
+    same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
+    assert same.all()
+
+
+def test_reference_golden_tests_still_hold(ref):
+    # the reference's own three tests (doppelspeller/tests/test_common.py:16-28)
+    title = '''LKJblksd skjasl dfkjf &* 8*&&&8 GGdjsdkj--sdsd-"sdi..//' d'  k   bkjh77_asda33'''
+    assert ref.common.transform_title(title) == 'lkjblksd skjasl dfkjf 88 ggdjsdkj sdsd sdi d k bkjh77asda33'
