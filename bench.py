@@ -32,6 +32,15 @@ METRIC = 'titles matched/sec vs 500k truth'
 UNIT = 'titles/s'
 
 
+_STDOUT = None
+
+
+def emit(line):
+    out = _STDOUT if _STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
 def log(*args):
     print(*args, file=sys.stderr, flush=True)
 
@@ -63,8 +72,16 @@ def time_cpu_port(index, sample, k):
     """The CPU port of match_maker.py:192-203 (oracle/ds_oracle.c, OpenMP over queries) on `sample`."""
     from oracle import oracle
     t0 = time.perf_counter()
-    rows, count, _ = oracle.topn(index, k, queries=sample)
+    rows, count, _ = oracle.topn(index, k, queries=sample, n_threads=host_threads())
     return time.perf_counter() - t0, rows, count
+
+
+def host_threads():
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which must not throttle the CPU arm)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 class ClockSampler:
@@ -137,7 +154,7 @@ def run_reference(args):
     times = [time_cpu_port(index, sample, args.top_n)[0] for _ in range(args.steps)]
     per_step = float(np.mean(times))
     value = len(sample) / per_step
-    cores = oracle.max_threads()
+    cores = host_threads()
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': per_step * 1e3, 'higher_is_better': True, 'scaling': 'strong',
@@ -149,7 +166,7 @@ def run_reference(args):
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, enc):
@@ -291,7 +308,7 @@ def run_ours(args):
         sample = cpu_sample(n_q, args.cpu_sample)
         time_cpu_port(index_cpu, sample[:64], k)
         seconds, want_rows, want_count = time_cpu_port(index_cpu, sample, k)
-        line['cpu_baseline'] = {'value': len(sample) / seconds, 'unit': UNIT, 'cores': oracle.max_threads(), 'kind': 'port',
+        line['cpu_baseline'] = {'value': len(sample) / seconds, 'unit': UNIT, 'cores': host_threads(), 'kind': 'port',
                                 'sample': f'{len(sample)} sampled queries x all {n_truth} truth rows, top-{k}, '
                                           f'{seconds:.1f}s; titles/s = sample / time (linear in Q)'}
         line['parity'].update({'checked_queries': int(len(sample)),
@@ -299,7 +316,7 @@ def run_ours(args):
         line['extra'] = pair_kernels(truth, test, rows_np, device)
     if world > 1:
         dist.destroy_process_group()
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def pair_kernels(truth, test, rows, device):
@@ -366,6 +383,11 @@ def main():
     parser.add_argument('--cpu-sample', type=int, default=2000)
     parser.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline / parity sample (profiling runs)')
     args = parser.parse_args()
+    # stdout must carry exactly one JSON line: libraries that print to fd 1 (NCCL's version banner) are
+    # diverted to stderr, the JSON goes to the original stdout
+    global _STDOUT
+    _STDOUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     import __graft_entry__ as entry
     lib = os.path.join(ROOT, 'doppelspeller_b200', '_lib', 'libdoppelspeller_b200.so')
     if not os.path.exists(lib) or not os.path.exists(os.path.join(ROOT, 'oracle', '_build', 'libds_oracle.so')):
