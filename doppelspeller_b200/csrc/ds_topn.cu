@@ -305,14 +305,35 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) k_scan(ScanParams p) {
     __syncthreads();
 
     // ---- stream the truth rows: one row per thread, all TQ queries at once ----
-    for (int row = cta_r0 + tid; row < cta_r1; row += THREADS) {
+    // Software pipelined: the next row's metadata and the next 16-byte chunk are requested before the
+    // current chunk is consumed (only 16 warps fit an SM at 128 registers, so latency is hidden by ILP).
+    int row = cta_r0 + tid;
+    uint32_t c0 = 0, c1 = 0;
+    float sum_t = 0.0f;
+    uint4 ch = make_uint4(0, 0, 0, 0);
+    if (row < cta_r1) {
+        c0 = p.chunk_ptr[row];
+        c1 = p.chunk_ptr[row + 1];
+        sum_t = p.sums[row];
+        if (c0 < c1) ch = __ldg(p.chunks + c0);
+    }
+    while (row < cta_r1) {
+        const int next_row = row + THREADS;
+        uint32_t n0 = 0, n1 = 0;
+        float next_sum = 0.0f;
+        if (next_row < cta_r1) {
+            n0 = p.chunk_ptr[next_row];
+            n1 = p.chunk_ptr[next_row + 1];
+            next_sum = p.sums[next_row];
+        }
         float sc[TQ];
 #pragma unroll
         for (int j = 0; j < TQ; ++j) sc[j] = 0.0f;
-        const uint32_t c0 = p.chunk_ptr[row], c1 = p.chunk_ptr[row + 1];
-        const float sum_t = p.sums[row];
+#pragma unroll 1
         for (uint32_t c = c0; c < c1; ++c) {
-            const uint4 ch = __ldg(p.chunks + c);
+            uint4 next_ch = make_uint4(0, 0, 0, 0);
+            if (c + 1 < c1) next_ch = __ldg(p.chunks + c + 1);
+            else if (n0 < n1) next_ch = __ldg(p.chunks + n0);
             const uint32_t words[4] = {ch.x, ch.y, ch.z, ch.w};
             uint2 ent[8];
 #pragma unroll
@@ -322,7 +343,9 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) k_scan(ScanParams p) {
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) accumulate_column(sc, ent[i].x, __uint_as_float(ent[i].y));
+            ch = next_ch;
         }
+        if (c0 == c1 && n0 < n1) ch = __ldg(p.chunks + n0);   // empty row: nothing was prefetched above
         if (p.dense != nullptr) {
 #pragma unroll
             for (int j = 0; j < TQ; ++j) {
@@ -330,16 +353,29 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) k_scan(ScanParams p) {
                 if (b >= 0) p.dense[(size_t)b * p.dense_stride + (row - p.r0)] = sc[j];
             }
         } else {
+            uint32_t pass = 0;
 #pragma unroll
             for (int j = 0; j < TQ; ++j) {
-                float2 ab = s_ab[j];
-                if (sc[j] > fmaf(ab.x, sum_t, ab.y)) {
-                    int b = s_qid[j];
-                    int pos = atomicAdd(p.cand_count + b, 1);
-                    if (pos < p.cap) p.cand[(size_t)b * p.cap + pos] = make_uint2((uint32_t)row, __float_as_uint(sc[j]));
+                const float2 ab = s_ab[j];
+                pass |= (sc[j] > fmaf(ab.x, sum_t, ab.y)) ? (1u << j) : 0u;
+            }
+            if (pass != 0) {   // rare: spill the accumulators once and emit the survivors
+                float spilled[TQ];
+#pragma unroll
+                for (int j = 0; j < TQ; ++j) spilled[j] = sc[j];
+                while (pass != 0) {
+                    const int j = __ffs(pass) - 1;
+                    pass &= pass - 1;
+                    const int b = s_qid[j];
+                    const int pos = atomicAdd(p.cand_count + b, 1);
+                    if (pos < p.cap) p.cand[(size_t)b * p.cap + pos] = make_uint2((uint32_t)row, __float_as_uint(spilled[j]));
                 }
             }
         }
+        row = next_row;
+        c0 = n0;
+        c1 = n1;
+        sum_t = next_sum;
     }
 }
 
