@@ -1,0 +1,123 @@
+"""bench_pairs.py - secondary benchmark: BASELINE.json configs[3] ("C4"), batched InDel ratio (K2) and the
+66-feature construct_features kernel (K3) over synthetic candidate pairs, titles up to 128 characters.
+
+    python bench_pairs.py [--pairs 100000000] [--steps 3] [--sample 200000]
+
+Pairs (seed 20240503): 90 % of the titles follow the example length distribution, 10 % are
+a stress slice with lengths uniform in [65, 128]; half of the pairs are candidate-like (a truth title and a
+misspelling of it), half are random.  Titles live in compact (bytes, offsets) tables in HBM, pairs are
+(title index, truth index) arrays - the B200 layout of the C ABI (`ds_*_pairs`).  Prints one JSON line with
+pairs/s, the algorithmic-byte HBM fraction of each kernel and a parity check of a sample against the CPU
+oracle.  Not the driver's headline bench (that is bench.py); kept for the "Levenshtein pairs/sec" metric.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+from collections import Counter
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def build_pairs(n_pairs, n_titles):
+    from doppelspeller_b200 import synthetic
+    rng = np.random.default_rng(synthetic.PAIRS_SEED)
+    n_long = n_titles // 10
+    truth = synthetic.generate_truth_titles(n_titles - n_long, seed=synthetic.PAIRS_SEED + 1)
+    truth += synthetic.generate_long_titles(n_long, seed=synthetic.PAIRS_SEED + 2)
+    test, source = synthetic.generate_test_titles(truth, n_titles, seed=synthetic.PAIRS_SEED + 3, matched=1.0)
+    idx_a = rng.integers(0, n_titles, size=n_pairs).astype(np.int32)
+    idx_b = np.where(rng.random(n_pairs) < 0.5, source[idx_a], rng.integers(0, n_titles, size=n_pairs)).astype(np.int32)
+    return truth, test, idx_a, idx_b
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--pairs', type=int, default=100_000_000)
+    parser.add_argument('--titles', type=int, default=400_000)
+    parser.add_argument('--steps', type=int, default=3)
+    parser.add_argument('--sample', type=int, default=200_000)
+    parser.add_argument('--chunk', type=int, default=25_000_000, help='pairs per kernel launch (bounds the 264 B/pair output)')
+    args = parser.parse_args()
+    import torch
+    from doppelspeller_b200 import _native as nat
+    from doppelspeller_b200 import feature_engineering as fe
+    from oracle import oracle
+    device = torch.device('cuda', 0)
+    t0 = time.time()
+    truth, test, idx_a, idx_b = build_pairs(args.pairs, args.titles)
+    counter = Counter(w for t in truth for w in set(t.split()))
+    counts = np.zeros((len(truth), 15), dtype=np.uint32)
+    for i, t in enumerate(truth):
+        ws = [counter[w] for w in t.split()[:15]]
+        counts[i, :len(ws)] = ws
+    codes_a, off_a = fe.encode_titles(test)
+    codes_b, off_b = fe.encode_titles(truth)
+    print(f'[bench_pairs] {args.pairs} pairs over {len(test)} + {len(truth)} titles built in {time.time() - t0:.1f}s', file=sys.stderr)
+    dev = lambda x: torch.as_tensor(x).to(device)   # noqa: E731
+    d = dict(a=dev(codes_a), oa=dev(off_a), b=dev(codes_b), ob=dev(off_b), c=dev(counts.view(np.int32)), ia=dev(idx_a), ib=dev(idx_b))
+    la = np.diff(off_a)[idx_a[:2_000_000]]
+    lb = np.diff(off_b)[idx_b[:2_000_000]]
+    mean_len = float((la + lb).mean())
+    chunk = min(args.chunk, args.pairs)
+    ratio = torch.empty(args.pairs, dtype=torch.uint8, device=device)
+    feats = torch.empty((chunk, 66), dtype=torch.float32, device=device)
+
+    def run_ratio():
+        nat.check(nat.lib.ds_indel_ratio_pairs(nat.ptr(d['a']), nat.ptr(d['oa']), len(test), nat.ptr(d['b']), nat.ptr(d['ob']), len(truth),
+                                               nat.ptr(d['ia']), nat.ptr(d['ib']), args.pairs, nat.ptr(ratio), None, nat.current_stream()))
+
+    def run_feats():
+        for c0 in range(0, args.pairs, chunk):
+            c1 = min(args.pairs, c0 + chunk)
+            fe.construct_features_pairs((d['a'], d['oa']), (d['b'], d['ob']), d['c'], d['ia'][c0:c1], d['ib'][c0:c1], fe.SPACE_CODE,
+                                        len(truth), response=feats[:c1 - c0])
+
+    peak = 6551.7
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        peak = float(json.load(open(path))['hbm_gbs'])
+    line = {'metric': 'Levenshtein pairs/sec', 'unit': 'pairs/s', 'pairs': args.pairs, 'data': 'synthetic',
+            'config': {'workload': f'C4 synthetic {args.pairs} candidate pairs, 10% titles in [65,128] chars (BASELINE.json configs[3])',
+                       'mean_la_plus_lb': mean_len}}
+    for name, fn, bpp in (('indel_ratio', run_ratio, mean_len + 3.0), ('construct_features', run_feats, mean_len + 2.0 + 60.0 + 264.0)):
+        fn()
+        torch.cuda.synchronize()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(args.steps):
+            fn()
+        stop.record()
+        stop.synchronize()
+        ms = start.elapsed_time(stop) / args.steps
+        line[name] = {'pairs_per_s': args.pairs / (ms / 1e3), 'ms': ms, 'algorithmic_bytes_per_pair': bpp,
+                      'hbm_frac': args.pairs * bpp / (ms / 1e3) / 1e9 / peak}
+    # parity of a sample against the oracle (padded layout on the CPU side)
+    n = min(args.sample, args.pairs, chunk)
+    sel = np.arange(n)
+    pa = np.zeros((n, 255), dtype=np.uint8)
+    pb = np.zeros((n, 255), dtype=np.uint8)
+    la_s = np.diff(off_a)[idx_a[sel]].astype(np.uint8)
+    lb_s = np.diff(off_b)[idx_b[sel]].astype(np.uint8)
+    for i in range(n):
+        pa[i, :la_s[i]] = codes_a[off_a[idx_a[i]]:off_a[idx_a[i] + 1]]
+        pb[i, :lb_s[i]] = codes_b[off_b[idx_b[i]]:off_b[idx_b[i] + 1]]
+    want_ratio = oracle.indel_ratio_u8_batch(pa, pb, la_s, lb_s)
+    want_feats = oracle.construct_features(la_s, lb_s, pa, pb, counts[idx_b[sel]], fe.SPACE_CODE, len(truth))
+    run_feats_first = fe.construct_features_pairs((d['a'], d['oa']), (d['b'], d['ob']), d['c'], d['ia'][:n], d['ib'][:n], fe.SPACE_CODE,
+                                                  len(truth)).cpu().numpy()
+    got_ratio = ratio[:n].cpu().numpy()
+    exact = (run_feats_first[:, :36] == want_feats[:, :36]) | (np.isnan(run_feats_first[:, :36]) & np.isnan(want_feats[:, :36]))
+    with np.errstate(all='ignore'):
+        close = np.isclose(run_feats_first[:, 36:], want_feats[:, 36:], rtol=1e-6, atol=0, equal_nan=True)
+    line['parity'] = {'sampled_pairs': int(n), 'ratio_mismatches': int((got_ratio != want_ratio).sum()),
+                      'integer_feature_mismatches': int((~exact).sum()), 'float_feature_mismatches': int((~close).sum())}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == '__main__':
+    main()

@@ -176,35 +176,170 @@ __device__ __forceinline__ void load_pair(const PairSource &s, int64_t p, const 
 // K2: one pair per lane
 //   mode 0: fast_levenshtein_ratio (uint8 wrap semantics)  -> out_u8 / out_dist
 //   mode 1: common.levenshtein_ratio on raw bytes          -> out_i32
+// Fast path (both strings <= 64 bytes, i.e. > 99 % of real titles): the strings are fetched with aligned
+// 32-bit loads into a per-lane shared-memory slot (odd word stride: conflict free), the match masks are
+// built and used from the lane's 40-entry column, nothing is re-read from global memory and the table is
+// never cleared (one pair per lane).  Everything else takes the general routines above.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(K2_BLOCK) k_indel_pairs(PairSource src, int64_t n, int mode, uint8_t *out_u8, uint16_t *out_dist,
-                                                          int32_t *out_i32) {
-    __shared__ u64 pm[PM_CODES * K2_BLOCK];
-    for (int i = threadIdx.x; i < PM_CODES * K2_BLOCK; i += K2_BLOCK) pm[i] = 0;
+// Pairs are first binned by length class so that the lanes of a warp run the same code path:
+//   class 0  both strings <= 64 bytes                       one 64-bit word, one pass
+//   class 1  both strings <= 128 bytes and la + lb <= 255   pattern in two 64-character blocks, carry replay
+//   class 2  everything else (uint8 wrap region, very long) general routines above
+template <int MAXLEN, int BLOCK>
+struct K2Smem {
+    static constexpr int STAGE_WORDS = ((MAXLEN + 6) / 4) | 1;   // aligned words covering MAXLEN bytes, odd lane stride
+    u64 pm[PM_CODES * BLOCK];
+    uint32_t stage_a[STAGE_WORDS * BLOCK];
+    uint32_t stage_b[STAGE_WORDS * BLOCK];
+    uint8_t lut[256];
+};
+
+// aligned 32-bit loads of the words covering [g, g + len); reads stay inside aligned words that hold at
+// least one valid byte, so they never leave the page of a valid byte
+__device__ __forceinline__ const uint8_t *stage_string(const uint8_t *g, int len, uint32_t *slot) {
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(g);
+    const int shift = (int)(addr & 3);
+    const uint32_t *g32 = reinterpret_cast<const uint32_t *>(addr - shift);
+    const int words = (shift + len + 3) >> 2;
+    for (int k = 0; k < words; ++k) slot[k] = __ldg(g32 + k);
+    return reinterpret_cast<const uint8_t *>(slot) + shift;
+}
+
+// LCS by the bit-vector recurrence on staged strings (m <= 128, n <= 128).  `lut` maps bytes to table
+// codes; a byte outside the table clears *ok (the caller falls back).  The lane's column is left dirty
+// unless CLEAN is set.
+template <int BLOCK, bool CLEAN>
+__device__ __forceinline__ int lcs_staged(u64 *pm, const uint8_t *pat, int m, const uint8_t *txt, int n, const uint8_t *lut, bool *ok) {
+    bool good = true;
+    int lcs = 0;
+    u64 carry_lo = 0, carry_hi = 0;   // carry out of the first block at text step j (j < 128)
+    for (int w0 = 0; w0 < m; w0 += 64) {
+        const int mw = min(64, m - w0);
+        for (int i = 0; i < mw; ++i) {
+            int c = lut[pat[w0 + i]];
+            good &= c < PM_CODES;
+            c = min(c, PM_CODES - 1);
+            pm[c * BLOCK] |= 1ull << i;
+        }
+        u64 v = ~0ull, out_lo = 0, out_hi = 0;
+        if (w0 == 0 && m <= 64) {
+            for (int j = 0; j < n; ++j) {
+                int c = lut[txt[j]];
+                good &= c < PM_CODES;
+                c = min(c, PM_CODES - 1);
+                const u64 mm = pm[c * BLOCK];
+                const u64 u = v & mm;
+                v = (v + u) | (v & ~mm);
+            }
+        } else {
+            for (int j = 0; j < n; ++j) {
+                int c = lut[txt[j]];
+                good &= c < PM_CODES;
+                c = min(c, PM_CODES - 1);
+                const u64 mm = pm[c * BLOCK];
+                const u64 u = v & mm;
+                const u64 cin = ((j < 64 ? carry_lo : carry_hi) >> (j & 63)) & 1ull;
+                const u64 s1 = v + u;
+                const u64 s2 = s1 + cin;
+                const u64 cout = (u64)((s1 < v) | (s2 < s1));
+                v = s2 | (v & ~mm);
+                if (j < 64) out_lo |= cout << j;
+                else out_hi |= cout << (j - 64);
+            }
+        }
+        carry_lo = out_lo;
+        carry_hi = out_hi;
+        const u64 valid = (mw == 64) ? ~0ull : ((1ull << mw) - 1);
+        lcs += __popcll(~v & valid);
+        if (CLEAN || w0 + 64 < m) {
+            for (int i = 0; i < mw; ++i) pm[min((int)lut[pat[w0 + i]], PM_CODES - 1) * BLOCK] = 0;
+        }
+    }
+    *ok = good;
+    return lcs;
+}
+
+__global__ void k_pair_classify(PairSource src, int64_t n, int32_t *__restrict__ lists, int *__restrict__ counts) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int cls = -1;
+    if (p < n) {
+        int la, lb;
+        if (src.stride > 0) {
+            la = src.la[p];
+            lb = src.lb[p];
+        } else {
+            const int64_t ia = src.idx_a[p], ib = src.idx_b[p];
+            la = (int)min((int64_t)DS_MAX_TITLE, src.off_a[ia + 1] - src.off_a[ia]);
+            lb = (int)min((int64_t)DS_MAX_TITLE, src.off_b[ib + 1] - src.off_b[ib]);
+        }
+        cls = (la <= 64 && lb <= 64) ? 0 : ((la <= 128 && lb <= 128 && la + lb <= 255) ? 1 : 2);
+    }
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const unsigned ballot = __ballot_sync(0xffffffffu, cls == c);
+        if (ballot == 0) continue;
+        int base = 0;
+        if (lane == __ffs(ballot) - 1) base = atomicAdd(counts + c, __popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
+        if (cls == c) lists[(size_t)c * n + base + __popc(ballot & ((1u << lane) - 1))] = (int32_t)p;
+    }
+}
+
+// mode 0: fast_levenshtein_ratio -> out_u8 / out_dist;  mode 1: common.levenshtein_ratio -> out_i32
+template <int MAXLEN, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_indel_pairs(PairSource src, const int32_t *__restrict__ pair_list, int64_t n, int mode,
+                                                       uint8_t *out_u8, uint16_t *out_dist, int32_t *out_i32) {
+    extern __shared__ __align__(16) unsigned char k2_raw[];
+    typedef K2Smem<MAXLEN, BLOCK> Smem;
+    Smem &sm = *reinterpret_cast<Smem *>(k2_raw);
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(sm.pm);
+        for (int i = threadIdx.x; i < (int)(sizeof(sm.pm) / 16); i += BLOCK) z[i] = make_uint4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < 256; i += BLOCK) sm.lut[i] = (uint8_t)min(255, map_code((uint8_t)i, mode));
+    }
     __syncthreads();
-    const int64_t p = (int64_t)blockIdx.x * K2_BLOCK + threadIdx.x;
-    if (p >= n) return;
+    const int64_t slot = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (slot >= n) return;
+    const int64_t p = pair_list ? (int64_t)pair_list[slot] : slot;
     const uint8_t *a, *b;
     int la, lb;
     int64_t tid_unused;
     load_pair(src, p, &a, &la, &b, &lb, &tid_unused);
-    u64 *my_pm = pm + threadIdx.x;
+    u64 *my_pm = sm.pm + threadIdx.x;
     const int total = la + lb;
+    int d = 0;
+    bool done = false;
+    if (MAXLEN > 0 && la <= MAXLEN && lb <= MAXLEN && (MAXLEN <= 64 || total <= 255)) {
+        const uint8_t *sa = stage_string(a, la, sm.stage_a + threadIdx.x * Smem::STAGE_WORDS);
+        const uint8_t *sb = stage_string(b, lb, sm.stage_b + threadIdx.x * Smem::STAGE_WORDS);
+        bool ok;
+        const int lcs = (la <= lb) ? lcs_staged<BLOCK, false>(my_pm, sa, la, sb, lb, sm.lut, &ok)
+                                   : lcs_staged<BLOCK, false>(my_pm, sb, lb, sa, la, sm.lut, &ok);
+        d = total - 2 * lcs;
+        done = ok;
+        if (!ok) {   // a byte outside the table polluted the lane's column: clean it for the general path
+            for (int c = 0; c < PM_CODES; ++c) my_pm[c * BLOCK] = 0;
+        }
+    }
     if (mode == 0) {
-        const bool ok = codes_in_table(a, la, 0) && codes_in_table(b, lb, 0);
-        const int d = indel_distance_u8<K2_BLOCK>(my_pm, a, la, b, lb, ok);
+        if (!done) {
+            const bool ok = codes_in_table(a, la, 0) && codes_in_table(b, lb, 0);
+            d = indel_distance_u8<BLOCK>(my_pm, a, la, b, lb, ok);
+        }
         out_u8[p] = (uint8_t)ratio_u8(total, d);
         if (out_dist) out_dist[p] = (uint16_t)d;
     } else {
         int result = 100;  // ratio 1.0 for two empty strings
         if (total > 0) {
-            const bool ok = codes_in_table(a, la, 1) && codes_in_table(b, lb, 1);
-            int d;
-            if (ok) {
-                int lcs = (la <= lb) ? lcs_bitvector<K2_BLOCK>(my_pm, a, la, b, lb, 1) : lcs_bitvector<K2_BLOCK>(my_pm, b, lb, a, la, 1);
-                d = total - 2 * lcs;
-            } else {
-                d = indel_true_dp(a, la, b, lb);
+            if (!done) {
+                const bool ok = codes_in_table(a, la, 1) && codes_in_table(b, lb, 1);
+                if (ok) {
+                    int lcs = (la <= lb) ? lcs_bitvector<BLOCK>(my_pm, a, la, b, lb, 1) : lcs_bitvector<BLOCK>(my_pm, b, lb, a, la, 1);
+                    d = total - 2 * lcs;
+                } else {
+                    d = indel_true_dp(a, la, b, lb);
+                }
             }
             // int(round(ratio * 100)): float64 divide, float64 multiply, round half to even
             const double ratio = __ddiv_rn((double)(total - d), (double)total);
@@ -412,11 +547,41 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k_features(PairSource src, cons
     }
 }
 
-static int launch_indel(const PairSource &src, int64_t n, int mode, uint8_t *out_u8, uint16_t *out_dist, int32_t *out_i32,
-                        cudaStream_t stream) {
+template <int MAXLEN, int BLOCK>
+static int launch_indel_class(const PairSource &src, const int32_t *list, int64_t n, int mode, uint8_t *out_u8, uint16_t *out_dist,
+                              int32_t *out_i32, cudaStream_t stream) {
     if (n <= 0) return DS_OK;
-    k_indel_pairs<<<(unsigned)ceil_div(n, K2_BLOCK), K2_BLOCK, 0, stream>>>(src, n, mode, out_u8, out_dist, out_i32);
+    const size_t smem = sizeof(K2Smem<MAXLEN, BLOCK>);
+    static bool attr_done = false;
+    if (!attr_done) {
+        DS_CUDA(cudaFuncSetAttribute(k_indel_pairs<MAXLEN, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    k_indel_pairs<MAXLEN, BLOCK><<<(unsigned)ceil_div(n, BLOCK), BLOCK, smem, stream>>>(src, list, n, mode, out_u8, out_dist, out_i32);
     DS_LAUNCHED("k_indel_pairs");
+    return DS_OK;
+}
+
+static int launch_indel(Workspace &ws, const PairSource &src, int64_t n, int mode, uint8_t *out_u8, uint16_t *out_dist, int32_t *out_i32) {
+    cudaStream_t stream = ws.stream();
+    if (n <= 0) return DS_OK;
+    if (n > INT32_MAX) return fail(DS_ERR_UNSUPPORTED, "more than 2^31-1 pairs per call");
+    if (n < 4096) {   // tiny batches: one launch, no binning
+        return launch_indel_class<64, K2_BLOCK>(src, nullptr, n, mode, out_u8, out_dist, out_i32, stream);
+    }
+    int32_t *d_lists = nullptr;
+    int *d_counts = nullptr;
+    DS_CHECK(ws.alloc(&d_lists, (size_t)3 * n));
+    DS_CHECK(ws.alloc(&d_counts, 3));
+    DS_CUDA(cudaMemsetAsync(d_counts, 0, 3 * sizeof(int), stream));
+    k_pair_classify<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(src, n, d_lists, d_counts);
+    DS_LAUNCHED("k_pair_classify");
+    int h_counts[3] = {0, 0, 0};
+    DS_CUDA(cudaMemcpyAsync(h_counts, d_counts, sizeof(h_counts), cudaMemcpyDeviceToHost, stream));
+    DS_CUDA(cudaStreamSynchronize(stream));
+    DS_CHECK((launch_indel_class<64, K2_BLOCK>(src, d_lists, h_counts[0], mode, out_u8, out_dist, out_i32, stream)));
+    DS_CHECK((launch_indel_class<128, 64>(src, d_lists + n, h_counts[1], mode, out_u8, out_dist, out_i32, stream)));
+    DS_CHECK((launch_indel_class<0, 64>(src, d_lists + 2 * n, h_counts[2], mode, out_u8, out_dist, out_i32, stream)));
     return DS_OK;
 }
 
@@ -481,7 +646,7 @@ int ds_indel_ratio_u8(const uint8_t *a, const uint8_t *b, int64_t stride, const 
     uint16_t *d_dist = nullptr;
     DS_CHECK(ws.stage_out(&d_ratio, out_ratio, (size_t)n));
     DS_CHECK(ws.stage_out(&d_dist, out_dist, (size_t)n));
-    DS_CHECK(launch_indel(src, n, 0, d_ratio, d_dist, nullptr, stream));
+    DS_CHECK(launch_indel(ws, src, n, 0, d_ratio, d_dist, nullptr));
     return ws.finish_outputs();
 }
 
@@ -512,7 +677,7 @@ int ds_indel_ratio_pairs(const uint8_t *bytes_a, const int64_t *offsets_a, int64
     uint16_t *d_dist = nullptr;
     DS_CHECK(ws.stage_out(&d_ratio, out_ratio, (size_t)n));
     DS_CHECK(ws.stage_out(&d_dist, out_dist, (size_t)n));
-    DS_CHECK(launch_indel(src, n, 0, d_ratio, d_dist, nullptr, stream));
+    DS_CHECK(launch_indel(ws, src, n, 0, d_ratio, d_dist, nullptr));
     return ws.finish_outputs();
 }
 
@@ -529,7 +694,7 @@ int ds_levenshtein_ratio_pairs(const uint8_t *bytes_a, const int64_t *offsets_a,
     DS_CHECK(pairs_source(ws, bytes_a, offsets_a, bytes_b, offsets_b, idx_a, idx_b, n, n_titles_a, n_titles_b, &src));
     int32_t *d_out = nullptr;
     DS_CHECK(ws.stage_out(&d_out, out, (size_t)n));
-    DS_CHECK(launch_indel(src, n, 1, nullptr, nullptr, d_out, stream));
+    DS_CHECK(launch_indel(ws, src, n, 1, nullptr, nullptr, d_out));
     return ws.finish_outputs();
 }
 
