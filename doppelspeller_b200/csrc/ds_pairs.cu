@@ -16,6 +16,8 @@
 // 64 characters at a time, the carry out of each text step being replayed as the carry in of the next
 // pass.  Only pairs that can wrap (la + lb > 255) or carry codes outside the 40-symbol table take the
 // literal uint8 DP.
+#include <cub/device/device_radix_sort.cuh>
+
 #include <cmath>
 
 #include "ds_common.cuh"
@@ -173,130 +175,212 @@ __device__ __forceinline__ void load_pair(const PairSource &s, int64_t p, const 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K2: one pair per lane
-//   mode 0: fast_levenshtein_ratio (uint8 wrap semantics)  -> out_u8 / out_dist
-//   mode 1: common.levenshtein_ratio on raw bytes          -> out_i32
-// Fast path (both strings <= 64 bytes, i.e. > 99 % of real titles): the strings are fetched with aligned
-// 32-bit loads into a per-lane shared-memory slot (odd word stride: conflict free), the match masks are
-// built and used from the lane's 40-entry column, nothing is re-read from global memory and the table is
-// never cleared (one pair per lane).  Everything else takes the general routines above.
+// K2: batched InDel ratio.
+//   MODE 0: fast_levenshtein_ratio (uint8 wrap semantics)  -> out_u8 / out_dist
+//   MODE 1: common.levenshtein_ratio on raw bytes          -> out_i32
+// Pairs are radix-sorted by (class, la + lb) so that the lanes of a warp run the same code path for about
+// the same number of steps:
+//   class 0  both strings <= 64 bytes: one pair per lane, one 64-bit word, one pass
+//   class 1  bit-vector path for longer strings (MODE 0: la + lb <= 255, MODE 1: all): one pair per lane,
+//            pattern in 64-character blocks, the carries of each text step replayed into the next block
+//   class 2  MODE 0 only, la + lb > 255 (uint8 cells can wrap): one pair per WARP, literal uint8 DP swept
+//            by anti-diagonals over 32-column strips
+// Strings are fetched with aligned 32-bit loads, re-aligned with funnel shifts and kept in a per-lane
+// shared-memory slot (odd word stride: conflict free), then consumed four characters per LDS.
 // ---------------------------------------------------------------------------------------------------
-// Pairs are first binned by length class so that the lanes of a warp run the same code path:
-//   class 0  both strings <= 64 bytes                       one 64-bit word, one pass
-//   class 1  both strings <= 128 bytes and la + lb <= 255   pattern in two 64-character blocks, carry replay
-//   class 2  everything else (uint8 wrap region, very long) general routines above
 template <int MAXLEN, int BLOCK>
 struct K2Smem {
-    static constexpr int STAGE_WORDS = ((MAXLEN + 6) / 4) | 1;   // aligned words covering MAXLEN bytes, odd lane stride
+    static constexpr int STAGE_WORDS = ((MAXLEN + 3) / 4) | 1;   // words per staged string, odd lane stride
     u64 pm[PM_CODES * BLOCK];
     uint32_t stage_a[STAGE_WORDS * BLOCK];
     uint32_t stage_b[STAGE_WORDS * BLOCK];
-    uint8_t lut[256];
 };
 
-// aligned 32-bit loads of the words covering [g, g + len); reads stay inside aligned words that hold at
-// least one valid byte, so they never leave the page of a valid byte
-__device__ __forceinline__ const uint8_t *stage_string(const uint8_t *g, int len, uint32_t *slot) {
+// Copies [g, g + len) into slot[0 .. ceil(len / 4)) so that byte i of the string is byte i of the slot.
+// Only aligned words holding at least one valid byte are read (never leaves the page of a valid byte).
+__device__ __forceinline__ void stage_string(const uint8_t *g, int len, uint32_t *slot) {
     const uintptr_t addr = reinterpret_cast<uintptr_t>(g);
     const int shift = (int)(addr & 3);
     const uint32_t *g32 = reinterpret_cast<const uint32_t *>(addr - shift);
-    const int words = (shift + len + 3) >> 2;
-    for (int k = 0; k < words; ++k) slot[k] = __ldg(g32 + k);
-    return reinterpret_cast<const uint8_t *>(slot) + shift;
+    const int words_out = (len + 3) >> 2;
+    const int words_in = (shift + len + 3) >> 2;
+    if (words_out == 0) return;
+    uint32_t cur = __ldg(g32);
+    for (int k = 0; k < words_out; ++k) {
+        uint32_t next = (k + 1 < words_in) ? __ldg(g32 + k + 1) : 0u;
+        slot[k] = __funnelshift_r(cur, next, shift * 8);
+        cur = next;
+    }
 }
 
-// LCS by the bit-vector recurrence on staged strings (m <= 128, n <= 128).  `lut` maps bytes to table
-// codes; a byte outside the table clears *ok (the caller falls back).  The lane's column is left dirty
-// unless CLEAN is set.
-template <int BLOCK, bool CLEAN>
-__device__ __forceinline__ int lcs_staged(u64 *pm, const uint8_t *pat, int m, const uint8_t *txt, int n, const uint8_t *lut, bool *ok) {
+template <int MODE>
+__device__ __forceinline__ int table_code(uint32_t byte, bool &good) {
+    int c = MODE == 0 ? (int)byte : map_code((uint8_t)byte, 1);
+    good &= c < PM_CODES;
+    return min(c, PM_CODES - 1);
+}
+
+// single-block LCS: pattern m <= 64 staged in `pat`, text n staged in `txt` (word-aligned slots)
+template <int BLOCK, int MODE>
+__device__ __forceinline__ int lcs_one_block(u64 *pm, const uint32_t *pat, int m, const uint32_t *txt, int n, bool *ok) {
+    bool good = true;
+    for (int i0 = 0; i0 < m; i0 += 4) {
+        uint32_t w = pat[i0 >> 2];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i0 + k < m) {
+                const int c = table_code<MODE>((w >> (8 * k)) & 0xffu, good);
+                pm[c * BLOCK] |= 1ull << (i0 + k);
+            }
+        }
+    }
+    u64 v = ~0ull;
+    for (int j0 = 0; j0 < n; j0 += 4) {
+        const uint32_t w = txt[j0 >> 2];
+        u64 mm[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            bool in_table = true;   // bytes past the end of the text are whatever follows it in memory: ignored
+            mm[k] = pm[table_code<MODE>((w >> (8 * k)) & 0xffu, in_table) * BLOCK];
+            good &= in_table | (j0 + k >= n);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (j0 + k < n) {
+                const u64 u = v & mm[k];
+                v = (v + u) | (v & ~mm[k]);
+            }
+        }
+    }
+    *ok = good;
+    const u64 valid = (m == 64) ? ~0ull : ((1ull << m) - 1);
+    return __popcll(~v & valid);
+}
+
+// general LCS: pattern m <= 255 in up to four 64-character blocks, text n <= 255
+template <int BLOCK, int MODE>
+__device__ int lcs_blocks(u64 *pm, const uint32_t *pat, int m, const uint32_t *txt, int n, bool *ok) {
     bool good = true;
     int lcs = 0;
-    u64 carry_lo = 0, carry_hi = 0;   // carry out of the first block at text step j (j < 128)
+    u64 carry[4] = {0, 0, 0, 0};
     for (int w0 = 0; w0 < m; w0 += 64) {
         const int mw = min(64, m - w0);
-        for (int i = 0; i < mw; ++i) {
-            int c = lut[pat[w0 + i]];
-            good &= c < PM_CODES;
-            c = min(c, PM_CODES - 1);
-            pm[c * BLOCK] |= 1ull << i;
-        }
-        u64 v = ~0ull, out_lo = 0, out_hi = 0;
-        if (w0 == 0 && m <= 64) {
-            for (int j = 0; j < n; ++j) {
-                int c = lut[txt[j]];
-                good &= c < PM_CODES;
-                c = min(c, PM_CODES - 1);
-                const u64 mm = pm[c * BLOCK];
-                const u64 u = v & mm;
-                v = (v + u) | (v & ~mm);
-            }
-        } else {
-            for (int j = 0; j < n; ++j) {
-                int c = lut[txt[j]];
-                good &= c < PM_CODES;
-                c = min(c, PM_CODES - 1);
-                const u64 mm = pm[c * BLOCK];
-                const u64 u = v & mm;
-                const u64 cin = ((j < 64 ? carry_lo : carry_hi) >> (j & 63)) & 1ull;
-                const u64 s1 = v + u;
-                const u64 s2 = s1 + cin;
-                const u64 cout = (u64)((s1 < v) | (s2 < s1));
-                v = s2 | (v & ~mm);
-                if (j < 64) out_lo |= cout << j;
-                else out_hi |= cout << (j - 64);
+        for (int i0 = 0; i0 < mw; i0 += 4) {
+            const uint32_t w = pat[(w0 + i0) >> 2];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (i0 + k < mw) {
+                    const int c = table_code<MODE>((w >> (8 * k)) & 0xffu, good);
+                    pm[c * BLOCK] |= 1ull << (i0 + k);
+                }
             }
         }
-        carry_lo = out_lo;
-        carry_hi = out_hi;
+        u64 v = ~0ull;
+        u64 out[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int seg = 0; seg < 4; ++seg) {
+            const u64 cw = carry[seg];
+            u64 ow = 0;
+            const int j_end = min(n, seg * 64 + 64);
+            for (int j0 = seg * 64; j0 < j_end; j0 += 4) {
+                const uint32_t w = txt[j0 >> 2];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (j0 + k < j_end) {
+                        const u64 mm = pm[table_code<MODE>((w >> (8 * k)) & 0xffu, good) * BLOCK];
+                        const u64 u = v & mm;
+                        const u64 cin = (cw >> ((j0 + k) & 63)) & 1ull;
+                        const u64 s1 = v + u;
+                        const u64 s2 = s1 + cin;
+                        ow |= (u64)((s1 < v) | (s2 < s1)) << ((j0 + k) & 63);
+                        v = s2 | (v & ~mm);
+                    }
+                }
+            }
+            out[seg] = ow;
+        }
+#pragma unroll
+        for (int seg = 0; seg < 4; ++seg) carry[seg] = out[seg];
         const u64 valid = (mw == 64) ? ~0ull : ((1ull << mw) - 1);
         lcs += __popcll(~v & valid);
-        if (CLEAN || w0 + 64 < m) {
-            for (int i = 0; i < mw; ++i) pm[min((int)lut[pat[w0 + i]], PM_CODES - 1) * BLOCK] = 0;
+        if (w0 + 64 < m) {   // the next block reuses the column
+            for (int i0 = 0; i0 < mw; i0 += 4) {
+                const uint32_t w = pat[(w0 + i0) >> 2];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    bool ignored = true;
+                    if (i0 + k < mw) pm[table_code<MODE>((w >> (8 * k)) & 0xffu, ignored) * BLOCK] = 0;
+                }
+            }
         }
     }
     *ok = good;
     return lcs;
 }
 
-__global__ void k_pair_classify(PairSource src, int64_t n, int32_t *__restrict__ lists, int *__restrict__ counts) {
+__device__ __forceinline__ void pair_lengths(const PairSource &src, int64_t p, int *la, int *lb) {
+    if (src.stride > 0) {
+        *la = src.la[p];
+        *lb = src.lb[p];
+    } else {
+        const int64_t ia = src.idx_a[p], ib = src.idx_b[p];
+        *la = (int)min((int64_t)DS_MAX_TITLE, src.off_a[ia + 1] - src.off_a[ia]);
+        *lb = (int)min((int64_t)DS_MAX_TITLE, src.off_b[ib + 1] - src.off_b[ib]);
+    }
+}
+
+__device__ __forceinline__ int pair_class(int la, int lb, int mode) {
+    if (la <= 64 && lb <= 64) return 0;
+    if (mode == 1 || la + lb <= 255) return 1;
+    return 2;
+}
+
+// sort key = (class << 9) | (la + lb); values = pair ids; counts per class
+__global__ void k_pair_keys(PairSource src, int64_t n, int mode, uint16_t *__restrict__ keys, int32_t *__restrict__ ids,
+                            int *__restrict__ counts) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int cls = -1;
     if (p < n) {
         int la, lb;
-        if (src.stride > 0) {
-            la = src.la[p];
-            lb = src.lb[p];
-        } else {
-            const int64_t ia = src.idx_a[p], ib = src.idx_b[p];
-            la = (int)min((int64_t)DS_MAX_TITLE, src.off_a[ia + 1] - src.off_a[ia]);
-            lb = (int)min((int64_t)DS_MAX_TITLE, src.off_b[ib + 1] - src.off_b[ib]);
-        }
-        cls = (la <= 64 && lb <= 64) ? 0 : ((la <= 128 && lb <= 128 && la + lb <= 255) ? 1 : 2);
+        pair_lengths(src, p, &la, &lb);
+        cls = pair_class(la, lb, mode);
+        keys[p] = (uint16_t)((cls << 9) | (la + lb));
+        ids[p] = (int32_t)p;
     }
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const unsigned ballot = __ballot_sync(0xffffffffu, cls == c);
-        if (ballot == 0) continue;
-        int base = 0;
-        if (lane == __ffs(ballot) - 1) base = atomicAdd(counts + c, __popc(ballot));
-        base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
-        if (cls == c) lists[(size_t)c * n + base + __popc(ballot & ((1u << lane) - 1))] = (int32_t)p;
+        if (ballot != 0 && lane == __ffs(ballot) - 1) atomicAdd(counts + c, __popc(ballot));
     }
 }
 
-// mode 0: fast_levenshtein_ratio -> out_u8 / out_dist;  mode 1: common.levenshtein_ratio -> out_i32
-template <int MAXLEN, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_indel_pairs(PairSource src, const int32_t *__restrict__ pair_list, int64_t n, int mode,
-                                                       uint8_t *out_u8, uint16_t *out_dist, int32_t *out_i32) {
+template <int MODE>
+__device__ __forceinline__ void store_result(int total, int d, int64_t p, uint8_t *out_u8, uint16_t *out_dist, int32_t *out_i32) {
+    if (MODE == 0) {
+        out_u8[p] = (uint8_t)ratio_u8(total, d);
+        if (out_dist) out_dist[p] = (uint16_t)d;
+    } else {
+        int result = 100;  // ratio 1.0 for two empty strings
+        if (total > 0) {
+            // int(round(ratio * 100)): float64 divide, float64 multiply, round half to even
+            const double ratio = __ddiv_rn((double)(total - d), (double)total);
+            result = (int)rint(__dmul_rn(ratio, 100.0));
+        }
+        out_i32[p] = result;
+    }
+}
+
+// classes 0 and 1: one pair per lane
+template <int MAXLEN, int BLOCK, int MODE>
+__global__ void __launch_bounds__(BLOCK) k_indel_pairs(PairSource src, const int32_t *__restrict__ pair_list, int64_t n, uint8_t *out_u8,
+                                                       uint16_t *out_dist, int32_t *out_i32) {
     extern __shared__ __align__(16) unsigned char k2_raw[];
     typedef K2Smem<MAXLEN, BLOCK> Smem;
     Smem &sm = *reinterpret_cast<Smem *>(k2_raw);
     {
         uint4 *z = reinterpret_cast<uint4 *>(sm.pm);
         for (int i = threadIdx.x; i < (int)(sizeof(sm.pm) / 16); i += BLOCK) z[i] = make_uint4(0, 0, 0, 0);
-        for (int i = threadIdx.x; i < 256; i += BLOCK) sm.lut[i] = (uint8_t)min(255, map_code((uint8_t)i, mode));
     }
     __syncthreads();
     const int64_t slot = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
@@ -310,42 +394,91 @@ __global__ void __launch_bounds__(BLOCK) k_indel_pairs(PairSource src, const int
     const int total = la + lb;
     int d = 0;
     bool done = false;
-    if (MAXLEN > 0 && la <= MAXLEN && lb <= MAXLEN && (MAXLEN <= 64 || total <= 255)) {
-        const uint8_t *sa = stage_string(a, la, sm.stage_a + threadIdx.x * Smem::STAGE_WORDS);
-        const uint8_t *sb = stage_string(b, lb, sm.stage_b + threadIdx.x * Smem::STAGE_WORDS);
+    if (la <= MAXLEN && lb <= MAXLEN && (MODE == 1 || MAXLEN <= 64 || total <= 255)) {
+        uint32_t *sa = sm.stage_a + threadIdx.x * Smem::STAGE_WORDS;
+        uint32_t *sb = sm.stage_b + threadIdx.x * Smem::STAGE_WORDS;
+        stage_string(a, la, sa);
+        stage_string(b, lb, sb);
         bool ok;
-        const int lcs = (la <= lb) ? lcs_staged<BLOCK, false>(my_pm, sa, la, sb, lb, sm.lut, &ok)
-                                   : lcs_staged<BLOCK, false>(my_pm, sb, lb, sa, la, sm.lut, &ok);
+        int lcs;
+        if (MAXLEN <= 64) lcs = (la <= lb) ? lcs_one_block<BLOCK, MODE>(my_pm, sa, la, sb, lb, &ok) : lcs_one_block<BLOCK, MODE>(my_pm, sb, lb, sa, la, &ok);
+        else lcs = (la <= lb) ? lcs_blocks<BLOCK, MODE>(my_pm, sa, la, sb, lb, &ok) : lcs_blocks<BLOCK, MODE>(my_pm, sb, lb, sa, la, &ok);
         d = total - 2 * lcs;
         done = ok;
         if (!ok) {   // a byte outside the table polluted the lane's column: clean it for the general path
             for (int c = 0; c < PM_CODES; ++c) my_pm[c * BLOCK] = 0;
         }
     }
-    if (mode == 0) {
-        if (!done) {
-            const bool ok = codes_in_table(a, la, 0) && codes_in_table(b, lb, 0);
-            d = indel_distance_u8<BLOCK>(my_pm, a, la, b, lb, ok);
-        }
-        out_u8[p] = (uint8_t)ratio_u8(total, d);
-        if (out_dist) out_dist[p] = (uint16_t)d;
-    } else {
-        int result = 100;  // ratio 1.0 for two empty strings
-        if (total > 0) {
-            if (!done) {
-                const bool ok = codes_in_table(a, la, 1) && codes_in_table(b, lb, 1);
-                if (ok) {
-                    int lcs = (la <= lb) ? lcs_bitvector<BLOCK>(my_pm, a, la, b, lb, 1) : lcs_bitvector<BLOCK>(my_pm, b, lb, a, la, 1);
-                    d = total - 2 * lcs;
-                } else {
-                    d = indel_true_dp(a, la, b, lb);
-                }
+    if (!done) {   // bytes outside the 40-symbol table (or an unsorted tiny batch): literal DP per lane
+        if (MODE == 0) d = (lb <= 255) ? indel_u8_dp(a, la, b, lb) : indel_u8_dp(b, lb, a, la);
+        else d = indel_true_dp(a, la, b, lb);
+    }
+    store_result<MODE>(total, d, p, out_u8, out_dist, out_i32);
+}
+
+// class 2 (MODE 0, la + lb > 255): the literal uint8 DP of feature_engineering.py:42-61, one pair per warp.
+// Columns are processed in strips of 32 (lane = column); inside a strip the cells of an anti-diagonal are
+// independent: at step s lane l owns row s - l + 1; `up` is its own previous cell, `left` / `diag` come from
+// lane l - 1 (shuffle) or, for the strip's first column, from the previous strip's last column kept in
+// shared memory.  Every cell is reduced mod 256 on store exactly like the uint8 matrix.
+struct WrapSmem {
+    uint8_t x[256];
+    uint8_t y[256];
+    uint8_t edge[2][260];
+};
+
+__global__ void __launch_bounds__(128) k_indel_wrap(PairSource src, const int32_t *__restrict__ pair_list, int64_t n, uint8_t *out_u8,
+                                                    uint16_t *out_dist) {
+    __shared__ WrapSmem smem[4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t slot = (int64_t)blockIdx.x * 4 + warp;
+    if (slot >= n) return;
+    WrapSmem &sm = smem[warp];
+    const int64_t p = pair_list ? (int64_t)pair_list[slot] : slot;
+    const uint8_t *a, *b;
+    int la, lb;
+    int64_t tid_unused;
+    load_pair(src, p, &a, &la, &b, &lb, &tid_unused);
+    // x = rows (outer sweep), y = columns (strips); fewer strips with the shorter string on the columns
+    const uint8_t *gx = (la >= lb) ? a : b, *gy = (la >= lb) ? b : a;
+    const int lx = max(la, lb), ly = min(la, lb);
+    for (int i = lane; i < lx; i += 32) sm.x[i] = gx[i];
+    for (int i = lane; i < ly; i += 32) sm.y[i] = gy[i];
+    for (int i = lane; i <= lx; i += 32) sm.edge[0][i] = (uint8_t)i;   // column 0: D[i][0] = i (uint8)
+    __syncwarp();
+    int result = lx & 0xff;   // ly == 0
+    int cur_edge = 0;
+    for (int c0 = 1; c0 <= ly; c0 += 32) {
+        const int j = c0 + lane;                       // this lane's column (1-based)
+        const bool active_col = j <= ly;
+        const uint8_t yj = active_col ? sm.y[j - 1] : 0;
+        int cur = j & 0xff;                            // D[0][j]
+        int prev_left = (j - 1) & 0xff;                // D[0][j-1]: the diagonal of row 1
+        const uint8_t *left_col = sm.edge[cur_edge];
+        uint8_t *next_col = sm.edge[cur_edge ^ 1];
+        const int last_lane = min(31, ly - c0);
+        if (lane == last_lane) next_col[0] = (uint8_t)cur;
+        for (int s = 0; s < lx + 31; ++s) {
+            const int i = s - lane + 1;                // row of this lane at this step
+            int left = __shfl_up_sync(0xffffffffu, cur, 1);
+            if (lane == 0) left = (i >= 1 && i <= lx) ? left_col[i] : 0;
+            if (i >= 1 && i <= lx && active_col) {
+                const int diag = prev_left + (sm.x[i - 1] == yj ? 0 : 2);
+                const int v = min(min(cur + 1, left + 1), diag) & 0xff;
+                prev_left = left;
+                cur = v;
+                if (lane == last_lane) next_col[i] = (uint8_t)v;
+            } else if (i < 1) {
+                prev_left = (lane == 0) ? left_col[0] : ((j - 1) & 0xff);
             }
-            // int(round(ratio * 100)): float64 divide, float64 multiply, round half to even
-            const double ratio = __ddiv_rn((double)(total - d), (double)total);
-            result = (int)rint(__dmul_rn(ratio, 100.0));
         }
-        out_i32[p] = result;
+        __syncwarp();
+        result = __shfl_sync(0xffffffffu, cur, last_lane);
+        cur_edge ^= 1;
+    }
+    if (lane == 0) {
+        out_u8[p] = (uint8_t)ratio_u8(la + lb, result);
+        if (out_dist) out_dist[p] = (uint16_t)result;
     }
 }
 
@@ -547,42 +680,60 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k_features(PairSource src, cons
     }
 }
 
-template <int MAXLEN, int BLOCK>
-static int launch_indel_class(const PairSource &src, const int32_t *list, int64_t n, int mode, uint8_t *out_u8, uint16_t *out_dist,
+template <int MAXLEN, int BLOCK, int MODE>
+static int launch_indel_class(const PairSource &src, const int32_t *list, int64_t n, uint8_t *out_u8, uint16_t *out_dist,
                               int32_t *out_i32, cudaStream_t stream) {
     if (n <= 0) return DS_OK;
     const size_t smem = sizeof(K2Smem<MAXLEN, BLOCK>);
     static bool attr_done = false;
     if (!attr_done) {
-        DS_CUDA(cudaFuncSetAttribute(k_indel_pairs<MAXLEN, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DS_CUDA((cudaFuncSetAttribute(k_indel_pairs<MAXLEN, BLOCK, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
         attr_done = true;
     }
-    k_indel_pairs<MAXLEN, BLOCK><<<(unsigned)ceil_div(n, BLOCK), BLOCK, smem, stream>>>(src, list, n, mode, out_u8, out_dist, out_i32);
+    k_indel_pairs<MAXLEN, BLOCK, MODE><<<(unsigned)ceil_div(n, BLOCK), BLOCK, smem, stream>>>(src, list, n, out_u8, out_dist, out_i32);
     DS_LAUNCHED("k_indel_pairs");
     return DS_OK;
 }
 
-static int launch_indel(Workspace &ws, const PairSource &src, int64_t n, int mode, uint8_t *out_u8, uint16_t *out_dist, int32_t *out_i32) {
+template <int MODE>
+static int launch_indel_mode(Workspace &ws, const PairSource &src, int64_t n, uint8_t *out_u8, uint16_t *out_dist, int32_t *out_i32) {
     cudaStream_t stream = ws.stream();
     if (n <= 0) return DS_OK;
     if (n > INT32_MAX) return fail(DS_ERR_UNSUPPORTED, "more than 2^31-1 pairs per call");
-    if (n < 4096) {   // tiny batches: one launch, no binning
-        return launch_indel_class<64, K2_BLOCK>(src, nullptr, n, mode, out_u8, out_dist, out_i32, stream);
-    }
-    int32_t *d_lists = nullptr;
+    uint16_t *d_keys = nullptr, *d_keys_sorted = nullptr;
+    int32_t *d_ids = nullptr, *d_ids_sorted = nullptr;
     int *d_counts = nullptr;
-    DS_CHECK(ws.alloc(&d_lists, (size_t)3 * n));
+    DS_CHECK(ws.alloc(&d_keys, (size_t)n));
+    DS_CHECK(ws.alloc(&d_keys_sorted, (size_t)n));
+    DS_CHECK(ws.alloc(&d_ids, (size_t)n));
+    DS_CHECK(ws.alloc(&d_ids_sorted, (size_t)n));
     DS_CHECK(ws.alloc(&d_counts, 3));
     DS_CUDA(cudaMemsetAsync(d_counts, 0, 3 * sizeof(int), stream));
-    k_pair_classify<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(src, n, d_lists, d_counts);
-    DS_LAUNCHED("k_pair_classify");
+    k_pair_keys<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(src, n, MODE, d_keys, d_ids, d_counts);
+    DS_LAUNCHED("k_pair_keys");
+    size_t temp_bytes = 0;
+    DS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, d_keys, d_keys_sorted, d_ids, d_ids_sorted, (int)n, 0, 11, stream));
+    unsigned char *d_temp = nullptr;
+    DS_CHECK(ws.alloc(&d_temp, temp_bytes));
+    DS_CUDA(cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, d_keys, d_keys_sorted, d_ids, d_ids_sorted, (int)n, 0, 11, stream));
+    g_kernel_launches.fetch_add(3);
     int h_counts[3] = {0, 0, 0};
     DS_CUDA(cudaMemcpyAsync(h_counts, d_counts, sizeof(h_counts), cudaMemcpyDeviceToHost, stream));
     DS_CUDA(cudaStreamSynchronize(stream));
-    DS_CHECK((launch_indel_class<64, K2_BLOCK>(src, d_lists, h_counts[0], mode, out_u8, out_dist, out_i32, stream)));
-    DS_CHECK((launch_indel_class<128, 64>(src, d_lists + n, h_counts[1], mode, out_u8, out_dist, out_i32, stream)));
-    DS_CHECK((launch_indel_class<0, 64>(src, d_lists + 2 * n, h_counts[2], mode, out_u8, out_dist, out_i32, stream)));
+    const int32_t *list = d_ids_sorted;
+    DS_CHECK((launch_indel_class<64, K2_BLOCK, MODE>(src, list, h_counts[0], out_u8, out_dist, out_i32, stream)));
+    DS_CHECK((launch_indel_class<255, 64, MODE>(src, list + h_counts[0], h_counts[1], out_u8, out_dist, out_i32, stream)));
+    if (h_counts[2] > 0) {
+        k_indel_wrap<<<(unsigned)ceil_div(h_counts[2], 4), 128, 0, stream>>>(src, list + h_counts[0] + h_counts[1], h_counts[2], out_u8,
+                                                                             out_dist);
+        DS_LAUNCHED("k_indel_wrap");
+    }
     return DS_OK;
+}
+
+static int launch_indel(Workspace &ws, const PairSource &src, int64_t n, int mode, uint8_t *out_u8, uint16_t *out_dist, int32_t *out_i32) {
+    return mode == 0 ? launch_indel_mode<0>(ws, src, n, out_u8, out_dist, out_i32)
+                     : launch_indel_mode<1>(ws, src, n, out_u8, out_dist, out_i32);
 }
 
 static int launch_features(const PairSource &src, const uint32_t *counts, int counts_per_truth, uint8_t space_code, uint32_t n_truth,
