@@ -92,6 +92,14 @@ __device__ __forceinline__ int ratio_u8(int total, int d) {
     return total == 0 ? 0 : ((100 * (total - d)) / total) & 0xff;
 }
 
+// Same value without an integer division: num = 100 * (L - d) <= 51,000 and L <= 510, so the float product
+// num * (1 / L) is within 1.3e-5 of the true quotient, whose fractional part is 0 or >= 1 / 510; the 1e-4 bias
+// therefore makes truncation exact.  Used where the ratio is evaluated per lane per round.
+__device__ __forceinline__ int ratio_u8_fast(int total, int d) {
+    const float q = fmaf((float)(100 * (total - d)), __frcp_rn((float)total), 1e-4f);
+    return total == 0 ? 0 : (__float2int_rz(q) & 0xff);
+}
+
 // literal restatement of the uint8 DP (feature_engineering.py:42-61), one thread; `y` (length ly <= 255)
 // indexes the row buffer, `x` the outer loop.  The recurrence is symmetric, so which string plays which
 // role does not change any cell value (the reference puts the shorter one on the rows, :35-37).
@@ -428,9 +436,9 @@ __global__ void __launch_bounds__(128) k_indel_wrap(PairSource src, const int32_
 constexpr int K3_WARPS = 8;
 
 struct K3Smem {
-    uint32_t pm_lo[PM_CODES];
-    uint32_t pm_hi[PM_CODES];
-    uint8_t a_ns[256];
+    uint32_t pm_lo[64];       // 40 codes used; 64 entries so that stale bytes read past a window stay in range
+    uint32_t pm_hi[64];
+    uint8_t a_ns[256 + 32];   // + 32: the uniform window loop may read (not use) up to 31 bytes past the end
     uint8_t b_cur[256];
     uint8_t recon[RECON_STRIDE];
 };
@@ -441,10 +449,11 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k_feature_words(PairSource src,
     __shared__ K3Smem smem[K3_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     K3Smem &sm = smem[warp];
-    for (int i = lane; i < PM_CODES; i += 32) {
+    for (int i = lane; i < 64; i += 32) {
         sm.pm_lo[i] = 0;
         sm.pm_hi[i] = 0;
     }
+    for (int i = lane; i < 256 + 32; i += 32) sm.a_ns[i] = 0;
     __syncwarp();
     const float nan_f = __int_as_float(0x7fc00000);
     const int64_t warps_total = (int64_t)gridDim.x * K3_WARPS;
@@ -507,11 +516,15 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k_feature_words(PairSource src,
                             const uint8_t *win = sm.a_ns + i;
                             int d;
                             if (fast && wl <= 32) {
+                                // uniform trip count (wl): tail windows stop updating once their characters run out;
+                                // reading a_ns a few bytes past n_ns stays inside the 256-byte buffer (i + wl <= 255 + 32)
                                 uint32_t v = ~0u;
-                                for (int j = 0; j < pl; ++j) {
-                                    const uint32_t mm = sm.pm_lo[win[j]];
+#pragma unroll 4
+                                for (int j = 0; j < wl; ++j) {
+                                    const uint32_t mm = sm.pm_lo[win[j] & 63];
                                     const uint32_t u = v & mm;
-                                    v = (v + u) | (v & ~mm);
+                                    const uint32_t nv = (v + u) | (v & ~mm);
+                                    v = (j < pl) ? nv : v;
                                 }
                                 const uint32_t valid = (wl == 32) ? ~0u : ((1u << wl) - 1);
                                 d = pl + wl - 2 * __popc(~v & valid);
@@ -528,7 +541,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k_feature_words(PairSource src,
                             } else {
                                 d = indel_u8_dp(word, wl, win, pl);   // words > 64 characters / bytes outside the table
                             }
-                            const int r = ratio_u8(pl + wl, d);
+                            const int r = ratio_u8_fast(pl + wl, d);
                             key = (r << 16) | (0xffff - i);  // max key = highest ratio, then lowest start
                         }
                         const int round_best = __reduce_max_sync(0xffffffffu, key);
@@ -551,8 +564,6 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k_feature_words(PairSource src,
                 if (lane == n_words) {
                     my_best = (float)best_ratio;
                     my_wlen = (float)wl;
-                    const uint32_t cnt = counts[truth_id * N_WORDS + n_words];
-                    my_idf = (float)log(__ddiv_rn((double)n_truth, (double)cnt));
                 }
                 // reconstructed title: best window (or a single space) followed by a space (:154-155)
                 if (best_start < 0) {
@@ -565,6 +576,10 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k_feature_words(PairSource src,
                 n_recon += 1;
                 ++n_words;
             }
+        }
+        if (lane < n_words) {   // idf of every found word at once (:153): log(N / count), count 0 -> +inf
+            const uint32_t cnt = counts[truth_id * N_WORDS + lane];
+            my_idf = (float)log(__ddiv_rn((double)n_truth, (double)cnt));
         }
         const int recon_n = n_recon > 0 ? n_recon - 1 : 0;   // drop the trailing space (:161)
         // IDF ranks (:158): NaN for every slot unless all 15 word slots are filled
