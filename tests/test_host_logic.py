@@ -1,0 +1,69 @@
+"""CPU: host-side logic of the drop-in layer (no kernels): canonical trigram encoding, the length
+pre-filter and the match selection of Prediction, title encoding, synthetic data determinism."""
+import numpy as np
+import pandas as pd
+
+from oracle import oracle
+
+
+def test_canonical_encoding_matches_get_n_grams():
+    from doppelspeller_b200 import encode, synthetic
+    truth = synthetic.generate_truth_titles(500, seed=5)
+    test, _ = synthetic.generate_test_titles(truth, 80, seed=6)
+    enc = encode.encode_canonical(test, truth)
+    vocab = [encode.trigram_text(c) for c in enc['vocab_codes']]
+    assert (np.diff(enc['vocab_codes']) > 0).all()          # column ids = ranks in code order (' ' < a..z < 0..9)
+    for i in (0, 7, 311, 499):
+        cols = enc['t_cols'][enc['t_ptr'][i]:enc['t_ptr'][i + 1]]
+        assert {vocab[c] for c in cols} == oracle.get_n_grams(truth[i], 3)          # common.py:150-151
+        assert (np.diff(cols.astype(np.int64)) > 0).all()
+    df = np.bincount(enc['t_cols'], minlength=len(vocab))
+    seen = df > 0
+    want = np.array([np.log(len(truth) / d) for d in df[seen]])
+    assert np.allclose(enc['idf64'][seen], want, rtol=0, atol=0) or np.array_equal(enc['idf64'][seen], want)
+    assert (enc['idf64'][~seen] == enc['idf64'][seen].max()).all()                 # match_maker.py:151,180-181
+
+
+def test_encode_title_docstring_vector():
+    from doppelspeller_b200 import feature_engineering as fe
+    assert fe.encode_title('coolblue bv')[:11].tolist() == [4, 16, 16, 13, 3, 13, 22, 6, 1, 3, 23]   # feature_engineering.py:28-29
+    codes, offsets = fe.encode_titles(['coolblue bv', 'abc'])
+    assert offsets.tolist() == [0, 11, 14] and codes[11:].tolist() == [2, 3, 4]
+    assert fe.FEATURES_COUNT == 66 and fe.SPACE_CODE == 1
+    assert fe.get_truth_words_counts('coolblue bv', {'coolblue': 1, 'bv': 2145})[:3].tolist() == [1, 2145, 0]
+
+
+def test_length_prefilter_matches_reference_formula():
+    from doppelspeller_b200 import predict
+    rng = np.random.default_rng(0)
+    la, lb = rng.integers(1, 256, 5000), rng.integers(1, 256, 5000)
+    got = predict.get_levenshtein_deletion_ratios(la, lb) < 94
+    want = np.array([((x + y - abs(x - y)) / (x + y)) * 100 < 94 for x, y in zip(la.tolist(), lb.tolist())])   # predict.py:140-151
+    assert np.array_equal(got, want)
+    assert all(bool(oracle.lib().orc_prefilter_rejects(int(x), int(y))) == w for x, y, w in zip(la[:500], lb[:500], want[:500]))
+
+
+def test_select_close_matches_follows_pandas_logic():
+    from doppelspeller_b200 import predict
+    rng = np.random.default_rng(1)
+    test_index = np.repeat(np.arange(200), 10)
+    ratios = rng.choice([0, 90, 94, 95, 96, 97, 100], size=2000, p=[0.6, 0.1, 0.05, 0.1, 0.05, 0.05, 0.05])
+    kept = predict.select_close_matches(test_index, ratios)
+    frame = pd.DataFrame({'test_index': test_index, 'ratio': ratios})
+    m = frame[frame['ratio'] > 94]
+    m = m[m.groupby('test_index')['ratio'].transform('max') == m['ratio']]          # predict.py:172-174
+    dup = m.loc[m.duplicated(['test_index']), 'test_index']                          # predict.py:158-161
+    m = m[~m['test_index'].isin(dup)]
+    assert np.array_equal(kept, m.index.to_numpy())
+
+
+def test_synthetic_generator_is_deterministic_and_normalised():
+    from doppelspeller_b200 import synthetic
+    a = synthetic.generate_truth_titles(300, seed=9)
+    assert a == synthetic.generate_truth_titles(300, seed=9)
+    t1, s1 = synthetic.generate_test_titles(a, 100, seed=10)
+    t2, s2 = synthetic.generate_test_titles(a, 100, seed=10)
+    assert t1 == t2 and np.array_equal(s1, s2)
+    for title in a + t1 + synthetic.generate_long_titles(20, seed=3):
+        assert 3 <= len(title) <= 255 and title == ' '.join(title.split())
+        assert set(title) <= set(' abcdefghijklmnopqrstuvwxyz0123456789')
