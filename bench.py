@@ -213,9 +213,11 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     shard = sharded.GpuShard(index, enc['q_ptr'], enc['q_cols']) if world > 1 else None
 
+    phase_ms = {} if os.environ.get('DS_PHASE_TIMING') else None
+
     def step_device():
         if world > 1:
-            rows, count, _ = sharded.sharded_topn(shard, k)
+            rows, count, _ = sharded.sharded_topn(shard, k, timings=phase_ms)
             return rows, count
         return index.topn(d_q_ptr, d_q_cols, k)
 
@@ -266,6 +268,8 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
     value = n_q / (ms_per_step / 1e3)
+    if phase_ms:
+        log(f'[bench] rank {rank} phase ms per step: ' + ', '.join(f'{k_}={v / (args.steps + args.warmup):.2f}' for k_, v in phase_ms.items()))
 
     for _ in range(min(args.warmup, 2)):
         step_e2e()

@@ -581,84 +581,125 @@ struct MergeParams {
     int *flagged_count;
 };
 
+// number of entries of the (score desc, row desc) sorted list [0, n) that are strictly better than (sc, rw)
+__device__ __forceinline__ int count_better(const double *__restrict__ score, const int64_t *__restrict__ row, int n, double sc,
+                                            int64_t rw) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (better(score[mid], row[mid], sc, rw)) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// One warp per query.  Every shard's list is sorted by (score desc, row desc) and shard s holds the rows of
+// the s-th contiguous ascending range, so: the global k-th best lies among the first k entries of each list and
+// its rank is a sum of binary searches; the qualifiers of a list are a prefix; and the k highest qualifying
+// rows are taken shard by shard from the highest range down.
 __global__ void __launch_bounds__(128) k_merge(MergeParams p) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int64_t q = blockIdx.x;
-    const int tid = threadIdx.x;
-    const int cap = p.n_shards * p.m;
-    double *u_score = reinterpret_cast<double *>(smem);
-    int64_t *u_row = reinterpret_cast<int64_t *>(smem + (size_t)cap * 8);
-    __shared__ int s_n, s_incomplete, s_nqual;
-    __shared__ double s_kth;
-    if (tid == 0) {
-        s_n = 0;
-        s_incomplete = 0;
-        s_nqual = 0;
-        s_kth = 0.0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * 4 + warp;
+    if (q >= p.n_q) return;
+    __shared__ int s_count[4][128];      // valid entries per shard (n_shards <= 128)
+    __shared__ int s_qual[4][128];       // qualifying entries per shard
+    __shared__ double s_kth[4];
+    int *n_valid = s_count[warp], *n_qual = s_qual[warp];
+    const size_t list_stride = (size_t)p.n_q * p.m;
+    const double *score_q = p.all_score + (size_t)q * p.m;
+    const int64_t *row_q = p.all_row + (size_t)q * p.m;
+
+    int positives = 0;
+    for (int s = lane; s < p.n_shards; s += 32) {
+        const int64_t *rows = row_q + s * list_stride;
+        int lo = 0, hi = p.m;                       // first unused slot (row < 0): slots are front packed
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (rows[mid] >= 0) lo = mid + 1;
+            else hi = mid;
+        }
+        n_valid[s] = lo;
+        positives += lo;
     }
-    __syncthreads();
-    for (int i = tid; i < cap; i += blockDim.x) {
-        int shard = i / p.m, slot = i % p.m;
-        size_t src = ((size_t)shard * p.n_q + q) * p.m + slot;
-        int64_t row = p.all_row[src];
-        if (row >= 0) {
-            int pos = atomicAdd(&s_n, 1);
-            u_score[pos] = p.all_score[src];
-            u_row[pos] = row;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) positives += __shfl_xor_sync(0xffffffffu, positives, d);
+    __syncwarp();
+
+    if (lane == 0) s_kth[warp] = 0.0;
+    __syncwarp();
+    if (positives >= p.k) {
+        // rank of every head element (slot < k of its list) in the union; exactly one has rank k - 1
+        const int heads = p.n_shards * p.k;
+        for (int e = lane; e < heads; e += 32) {
+            const int s = e / p.k, i = e % p.k;
+            if (i >= n_valid[s]) continue;
+            const double sc = score_q[s * list_stride + i];
+            const int64_t rw = row_q[s * list_stride + i];
+            int rank = i;
+            for (int t = 0; t < p.n_shards && rank < p.k; ++t) {
+                if (t == s) continue;
+                rank += count_better(score_q + t * list_stride, row_q + t * list_stride, n_valid[t], sc, rw);
+            }
+            if (rank == p.k - 1) s_kth[warp] = sc;
         }
     }
-    __syncthreads();
-    const int n = s_n;
-    if (n >= p.k) {
-        for (int i = tid; i < n; i += blockDim.x) {
-            int rank = 0;
-            const double si = u_score[i];
-            const int64_t ri = u_row[i];
-            for (int j = 0; j < n; ++j) rank += better(u_score[j], u_row[j], si, ri);
-            if (rank == p.k - 1) s_kth = si;
-        }
-    }
-    __syncthreads();
-    const float kth_key = (n >= p.k) ? __double2float_rn(s_kth) : 0.0f;
+    __syncwarp();
+    const float kth_key = (positives >= p.k) ? __double2float_rn(s_kth[warp]) : 0.0f;
     const double thr = threshold_from_key(kth_key);
-    int64_t *rows = p.out_rows + q * p.k;
+    int64_t *rows_out = p.out_rows + q * p.k;
     int flags = 0;
     if (!(thr > 0.0)) {
         // every row with a non-NaN score qualifies (scores are >= 0): the last k rows of the DB, unless the
         // query has mx == 0, where rows with sums == 0 score 0/0 = NaN and must be skipped by the rescan.
         flags = DS_FLAG_FEW_POSITIVE;
-        bool nan_risk = (p.q_mx != nullptr) && (p.q_mx[q] == 0.0);
-        if (nan_risk) flags |= DS_FLAG_RESCAN;
-        int64_t count = min((int64_t)p.k, p.n_total);
-        for (int i = tid; i < p.k; i += blockDim.x) rows[i] = (i < count) ? (p.n_total - 1 - i) : -1;
-        if (tid == 0) p.out_count[q] = (int32_t)count;
+        if ((p.q_mx != nullptr) && (p.q_mx[q] == 0.0)) flags |= DS_FLAG_RESCAN;
+        const int64_t count = min((int64_t)p.k, p.n_total);
+        for (int i = lane; i < p.k; i += 32) rows_out[i] = (i < count) ? (p.n_total - 1 - i) : -1;
+        if (lane == 0) p.out_count[q] = (int32_t)count;
     } else {
-        // a shard whose list is full may hold further qualifiers iff its lowest retained score qualifies
-        if (tid < p.n_shards) {
-            size_t last = ((size_t)tid * p.n_q + q) * p.m + (p.m - 1);
-            if (p.all_row[last] >= 0 && p.all_score[last] >= thr) s_incomplete = 1;
-        }
-        __syncthreads();
-        if (s_incomplete) {
-            flags = DS_FLAG_RESCAN;
-            for (int i = tid; i < p.k; i += blockDim.x) rows[i] = -1;
-            if (tid == 0) p.out_count[q] = 0;
-        } else {
-            for (int i = tid; i < p.k; i += blockDim.x) rows[i] = -1;
-            __syncthreads();
-            for (int i = tid; i < n; i += blockDim.x) {
-                if (!(u_score[i] >= thr)) continue;
-                atomicAdd(&s_nqual, 1);
-                int rank = 0;
-                const int64_t ri = u_row[i];
-                for (int j = 0; j < n; ++j) rank += (u_score[j] >= thr) && (u_row[j] > ri);
-                if (rank < p.k) rows[rank] = ri;
+        int incomplete = 0, total_qual = 0;
+        for (int s = lane; s < p.n_shards; s += 32) {
+            const double *scores = score_q + s * list_stride;
+            int lo = 0, hi = n_valid[s];            // qualifiers = prefix with score >= thr
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (scores[mid] >= thr) lo = mid + 1;
+                else hi = mid;
             }
-            __syncthreads();
-            if (tid == 0) p.out_count[q] = min(s_nqual, p.k);
+            n_qual[s] = lo;
+            total_qual += lo;
+            // a full list whose lowest entry still qualifies may have dropped further qualifiers
+            incomplete |= (n_valid[s] == p.m && lo == p.m);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            total_qual += __shfl_xor_sync(0xffffffffu, total_qual, d);
+            incomplete |= __shfl_xor_sync(0xffffffffu, incomplete, d);
+        }
+        __syncwarp();
+        for (int i = lane; i < p.k; i += 32) rows_out[i] = -1;
+        __syncwarp();
+        if (incomplete) {
+            flags = DS_FLAG_RESCAN;
+            if (lane == 0) p.out_count[q] = 0;
+        } else {
+            int filled = 0;
+            for (int s = p.n_shards - 1; s >= 0 && filled < p.k; --s) {
+                const int c = n_qual[s];
+                const int64_t *rows = row_q + s * list_stride;
+                const int room = p.k - filled;
+                for (int i = lane; i < c; i += 32) {
+                    const int64_t ri = rows[i];
+                    int rank = 0;
+                    for (int j = 0; j < c; ++j) rank += rows[j] > ri;
+                    if (rank < room) rows_out[filled + rank] = ri;
+                }
+                filled += min(c, room);
+            }
+            if (lane == 0) p.out_count[q] = min(total_qual, p.k);
         }
     }
-    if (tid == 0) {
+    if (lane == 0) {
         if (p.out_kth) p.out_kth[q] = kth_key;
         if (p.out_threshold) p.out_threshold[q] = thr;
         if (p.out_flags) p.out_flags[q] = flags;
@@ -991,17 +1032,8 @@ static int merge_topn(cudaStream_t stream, int n_shards, int64_t n_q, int k, int
     mp.out_threshold = d_out_threshold;
     mp.out_flags = d_out_flags;
     mp.flagged_count = d_flagged_count;
-    size_t smem = (size_t)n_shards * m * 16;
-    static size_t attr_bytes = 0;
-    if (smem > 48 * 1024 && smem > attr_bytes) {
-        if (smem > 227 * 1024) return fail(DS_ERR_UNSUPPORTED, "n_shards * retained (%d * %d) too large for the merge kernel", n_shards, m);
-        DS_CUDA(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_bytes = smem;
-    }
-    for (int64_t q0 = 0; q0 < n_q; q0 += 1 << 30) {  // grid.x limit is 2^31-1; kept for symmetry
-        k_merge<<<(unsigned)std::min<int64_t>(n_q - q0, 1 << 30), 128, smem, stream>>>(mp);
-        DS_LAUNCHED("k_merge");
-    }
+    k_merge<<<(unsigned)ceil_div(n_q, 4), 128, 0, stream>>>(mp);
+    DS_LAUNCHED("k_merge");
     return DS_OK;
 }
 

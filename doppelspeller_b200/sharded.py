@@ -94,23 +94,42 @@ def _all_gather(tensor, group, world):
     return flat.view((world,) + tuple(tensor.shape))
 
 
-def sharded_topn(shard, k, group=None):
+def sharded_topn(shard, k, group=None, timings=None):
     """Runs the three phases on this rank's `shard` (GpuShard or any object with local / merge / rescan).
     Returns (rows int64[Q,k] global truth rows in descending order, count int32[Q], flags int32[Q]) -
-    identical on every rank."""
+    identical on every rank.  `timings` (dict) receives per-phase milliseconds when given (CUDA tensors only)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+
+    marks = []
+
+    def mark(name):
+        if timings is not None and torch.cuda.is_available():
+            event = torch.cuda.Event(enable_timing=True)
+            event.record()
+            marks.append((name, event))
+
+    mark('start')
     score, row, mx = shard.local(k)
+    mark('local')
     all_score = _all_gather(score, group, world)
     all_row = _all_gather(row, group, world)
+    mark('all_gather')
     rows, count, _, threshold, flags = shard.merge(all_score, all_row, k, mx)
+    mark('merge')
     flagged = torch.nonzero((flags & nat.DS_FLAG_RESCAN) != 0).flatten()
     if flagged.numel() > 0:          # the same set on every rank: merge inputs are replicated
         local_rows, local_count = shard.rescan(mx, threshold, flags, k)
+        mark('rescan')
         per_rows = _all_gather(local_rows[flagged], group, world)
         per_count = _all_gather(local_count[flagged], group, world)
         fixed_rows, fixed_count = combine_rescans(per_rows, per_count, k)
         rows[flagged] = fixed_rows
         count[flagged] = fixed_count
+        mark('rescan_exchange')
+    if timings is not None and marks:
+        marks[-1][1].synchronize()
+        for (_, before), (name, after) in zip(marks[:-1], marks[1:]):
+            timings[name] = timings.get(name, 0.0) + before.elapsed_time(after)
     return rows, count, flags
