@@ -28,6 +28,7 @@ EXPORTED_SYMBOLS = (
     'ds_topn', 'ds_topn_retained', 'ds_topn_local', 'ds_topn_merge', 'ds_topn_rescan',
     'ds_indel_ratio_u8', 'ds_indel_ratio_pairs', 'ds_levenshtein_ratio_pairs',
     'ds_construct_features', 'ds_construct_features_pairs',
+    'ds_encode_max_vocab', 'ds_encode_trigrams',
 )
 
 
@@ -51,6 +52,9 @@ lib.ds_last_error.restype = ctypes.c_char_p
 lib.ds_kernel_launches.restype = _i64
 lib.ds_topn_retained.restype = _i32
 lib.ds_topn_retained.argtypes = [_i32]
+lib.ds_encode_max_vocab.restype = _i32
+lib.ds_encode_trigrams.argtypes = [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_i32),
+                                   ctypes.POINTER(_i64), ctypes.POINTER(_i64), ctypes.c_int, _vp]
 lib.ds_index_create.argtypes = [ctypes.POINTER(_vp), ctypes.c_int, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _i64, _vp]
 lib.ds_index_destroy.argtypes = [_vp]
 lib.ds_index_get_sums.argtypes = [_vp, _vp, _vp]
@@ -64,7 +68,7 @@ lib.ds_levenshtein_ratio_pairs.argtypes = [_vp, _vp, _i64, _vp, _vp, _i64, _vp, 
 lib.ds_construct_features.argtypes = [_vp, _vp, _vp, _vp, _i64, _vp, _u8, _u32, _i64, _vp, _vp]
 lib.ds_construct_features_pairs.argtypes = [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _u8, _u32, _i64, _vp, _vp]
 for _name in EXPORTED_SYMBOLS:
-    if _name not in ('ds_last_error', 'ds_kernel_launches', 'ds_topn_retained', 'ds_version'):
+    if _name not in ('ds_last_error', 'ds_kernel_launches', 'ds_topn_retained', 'ds_version', 'ds_encode_max_vocab'):
         getattr(lib, _name).restype = ctypes.c_int
 
 

@@ -1,0 +1,257 @@
+// ds_encode.cu - index build, host-preprocessing half moved to the GPU:
+// titles -> per-title trigram SETS -> canonical column ids -> document frequencies -> idf.
+//
+// Reference semantics (paths relative to /root/reference):
+//   common.get_n_grams            doppelspeller/common.py:150-151   every 3-character window, as a set
+//   common.get_n_grams_counter    doppelspeller/common.py:145-147   document frequency over the per-title sets
+//   MatchMaker._idf_n_gram        doppelspeller/match_maker.py:135-142   idf = math.log(N / df)
+//   MatchMaker._get_encoding_values  match_maker.py:149-153  query-only n-grams weigh max(idf)  (:95,:180-181)
+// The reference numbers the columns by python set iteration order (:144-147), which depends on
+// PYTHONHASHSEED; this encoder uses the canonical order instead (column id = rank of the trigram code
+// c0 * 37^2 + c1 * 37 + c2 over the alphabet ' a..z0..9'), the order `encode.encode_canonical` defines on
+// the host and every benchmark uses.  `MatchMaker.__init__` keeps the reference's own order for bit-parity
+// with one particular reference process.
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "ds_common.cuh"
+
+namespace ds {
+
+constexpr int ENC_BASE = 37;
+constexpr int ENC_CODES = ENC_BASE * ENC_BASE * ENC_BASE;   // 50,653 possible trigrams
+constexpr int ENC_WARPS = 4;
+
+__device__ __forceinline__ int enc_symbol(uint8_t c) {
+    if (c == ' ') return 0;
+    if (c >= 'a' && c <= 'z') return c - 'a' + 1;
+    if (c >= '0' && c <= '9') return c - '0' + 27;
+    return -1;
+}
+
+// One warp per title.  PASS 0: number of distinct trigrams.  PASS 1: the distinct trigram codes, ascending,
+// at out[ptr[title] ..); presence flags; document frequencies (truth titles only).
+template <int PASS>
+__global__ void __launch_bounds__(ENC_WARPS * 32) k_trigrams(const uint8_t *__restrict__ bytes, const int64_t *__restrict__ offsets,
+                                                            int64_t n_titles, int64_t *__restrict__ counts,
+                                                            const int64_t *__restrict__ ptr, uint16_t *__restrict__ out,
+                                                            int *__restrict__ present, int *__restrict__ df, int *__restrict__ bad) {
+    __shared__ int s_code[ENC_WARPS][256];
+    __shared__ bool s_first[ENC_WARPS][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t t = (int64_t)blockIdx.x * ENC_WARPS + warp;
+    if (t >= n_titles) return;
+    int *code = s_code[warp];
+    bool *is_first = s_first[warp];
+    const int64_t o = offsets[t];
+    const int len = (int)min((int64_t)DS_MAX_TITLE, offsets[t + 1] - o);
+    const int g = max(len - 2, 0);
+    for (int i = lane; i < g; i += 32) {
+        const int a = enc_symbol(bytes[o + i]), b = enc_symbol(bytes[o + i + 1]), c = enc_symbol(bytes[o + i + 2]);
+        if ((a | b | c) < 0) atomicExch(bad, 1);
+        code[i] = (max(a, 0) * ENC_BASE + max(b, 0)) * ENC_BASE + max(c, 0);
+    }
+    __syncwarp();
+    // set semantics (common.py:150-151): keep the first occurrence of every code
+    int n_unique = 0;
+    for (int i0 = 0; i0 < g; i0 += 32) {
+        const int i = i0 + lane;
+        bool first = false;
+        if (i < g) {
+            const int x = code[i];
+            first = true;
+            for (int j = 0; j < i; ++j) first &= code[j] != x;
+            if (PASS == 1) is_first[i] = first;
+        }
+        n_unique += __popc(__ballot_sync(0xffffffffu, first));
+    }
+    if (PASS == 1) {
+        __syncwarp();
+        for (int i = lane; i < g; i += 32) {
+            if (!is_first[i]) continue;
+            const int x = code[i];
+            int rank = 0;                                            // ascending position among the distinct codes
+            for (int j = 0; j < g; ++j) rank += is_first[j] && code[j] < x;
+            out[ptr[t] + rank] = (uint16_t)x;
+            present[x] = 1;
+            if (df != nullptr) atomicAdd(df + x, 1);
+        }
+    }
+    if (PASS == 0 && lane == 0) counts[t] = n_unique;
+}
+
+__global__ void k_remap(uint16_t *__restrict__ cols, int64_t n, const int *__restrict__ new_id) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cols[i] = (uint16_t)new_id[cols[i]];
+}
+
+__global__ void k_vocab(const int *__restrict__ present, const int *__restrict__ new_id, const int *__restrict__ df,
+                        int32_t *__restrict__ vocab_codes, int *__restrict__ df_by_col) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < ENC_CODES && present[c]) {
+        vocab_codes[new_id[c]] = c;
+        df_by_col[new_id[c]] = df[c];
+    }
+}
+
+static int exclusive_sum_i64(Workspace &ws, const int64_t *in, int64_t *out, int64_t n) {
+    size_t temp_bytes = 0;
+    DS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, in, out, (int)n, ws.stream()));
+    unsigned char *temp = nullptr;
+    DS_CHECK(ws.alloc(&temp, temp_bytes));
+    DS_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, in, out, (int)n, ws.stream()));
+    g_kernel_launches.fetch_add(1);
+    return DS_OK;
+}
+
+// trigram CSR of one title collection: row_ptr [n + 1], cols (trigram codes, ascending per title)
+static int encode_side(Workspace &ws, const uint8_t *d_bytes, const int64_t *d_offsets, int64_t n, int64_t *d_row_ptr, uint16_t *d_cols,
+                       int *d_present, int *d_df, int *d_bad, int64_t *nnz) {
+    cudaStream_t stream = ws.stream();
+    *nnz = 0;
+    if (n == 0) {
+        DS_CUDA(cudaMemsetAsync(d_row_ptr, 0, 8, stream));
+        return DS_OK;
+    }
+    int64_t *d_counts = nullptr;
+    DS_CHECK(ws.alloc(&d_counts, (size_t)n + 1));
+    DS_CUDA(cudaMemsetAsync(d_counts + n, 0, 8, stream));
+    const unsigned blocks = (unsigned)ceil_div(n, ENC_WARPS);
+    k_trigrams<0><<<blocks, ENC_WARPS * 32, 0, stream>>>(d_bytes, d_offsets, n, d_counts, nullptr, nullptr, nullptr, nullptr, d_bad);
+    DS_LAUNCHED("k_trigrams<0>");
+    DS_CHECK(exclusive_sum_i64(ws, d_counts, d_row_ptr, n + 1));
+    k_trigrams<1><<<blocks, ENC_WARPS * 32, 0, stream>>>(d_bytes, d_offsets, n, nullptr, d_row_ptr, d_cols, d_present, d_df, d_bad);
+    DS_LAUNCHED("k_trigrams<1>");
+    DS_CUDA(cudaMemcpyAsync(nnz, d_row_ptr + n, 8, cudaMemcpyDeviceToHost, stream));
+    DS_CUDA(cudaStreamSynchronize(stream));
+    return DS_OK;
+}
+
+}  // namespace ds
+
+using namespace ds;
+
+extern "C" {
+
+int32_t ds_encode_max_vocab(void) { return ENC_CODES; }
+
+int ds_encode_trigrams(const uint8_t *truth_bytes, const int64_t *truth_offsets, int64_t n_truth, const uint8_t *query_bytes,
+                       const int64_t *query_offsets, int64_t n_queries, int64_t *t_row_ptr, uint16_t *t_col_ids,
+                       int64_t *q_row_ptr, uint16_t *q_col_ids, double *idf64_by_col, int32_t *vocab_codes, int32_t *out_n_vocab,
+                       int64_t *out_truth_nnz, int64_t *out_query_nnz, int device, void *stream_) {
+    if (n_truth < 1 || n_queries < 0) return fail(DS_ERR_BAD_ARG, "n_truth < 1 or n_queries < 0");
+    if (!truth_bytes || !truth_offsets || !t_row_ptr || !t_col_ids || !q_row_ptr || !idf64_by_col || !vocab_codes || !out_n_vocab ||
+        !out_truth_nnz || !out_query_nnz)
+        return fail(DS_ERR_BAD_ARG, "NULL argument");
+    if (n_queries > 0 && (!query_bytes || !query_offsets || !q_col_ids)) return fail(DS_ERR_BAD_ARG, "NULL query argument");
+    int n_devices = 0;
+    if (cudaGetDeviceCount(&n_devices) != cudaSuccess || n_devices == 0) {
+        cudaGetLastError();
+        return fail(DS_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    DeviceGuard guard(device);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    Workspace ws(stream);
+
+    // byte totals (to size the staging of host inputs and the capacity of the outputs)
+    auto last_offset = [&](const int64_t *offsets, int64_t n, int64_t *total) -> int {
+        if (is_device_pointer(offsets)) {
+            DS_CUDA(cudaMemcpyAsync(total, offsets + n, 8, cudaMemcpyDeviceToHost, stream));
+            DS_CUDA(cudaStreamSynchronize(stream));
+        } else {
+            *total = offsets[n];
+        }
+        return DS_OK;
+    };
+    int64_t truth_total = 0, query_total = 0;
+    DS_CHECK(last_offset(truth_offsets, n_truth, &truth_total));
+    if (n_queries > 0) DS_CHECK(last_offset(query_offsets, n_queries, &query_total));
+
+    const uint8_t *d_tb = nullptr, *d_qb = nullptr;
+    const int64_t *d_to = nullptr, *d_qo = nullptr;
+    DS_CHECK(ws.stage_in(&d_tb, truth_bytes, (size_t)std::max<int64_t>(1, truth_total)));
+    DS_CHECK(ws.stage_in(&d_to, truth_offsets, (size_t)n_truth + 1));
+    if (n_queries > 0) {
+        DS_CHECK(ws.stage_in(&d_qb, query_bytes, (size_t)std::max<int64_t>(1, query_total)));
+        DS_CHECK(ws.stage_in(&d_qo, query_offsets, (size_t)n_queries + 1));
+    }
+    // outputs: capacity of the column arrays = total title bytes (a title of L characters has <= L - 2 trigrams)
+    int64_t *d_tp = nullptr, *d_qp = nullptr;
+    uint16_t *d_tc = nullptr, *d_qc = nullptr;
+    double *d_idf = nullptr;
+    int32_t *d_vocab = nullptr;
+    DS_CHECK(ws.stage_out(&d_tp, t_row_ptr, (size_t)n_truth + 1));
+    DS_CHECK(ws.stage_out(&d_tc, t_col_ids, (size_t)std::max<int64_t>(1, truth_total)));
+    DS_CHECK(ws.stage_out(&d_qp, q_row_ptr, (size_t)n_queries + 1));
+    if (n_queries > 0) DS_CHECK(ws.stage_out(&d_qc, q_col_ids, (size_t)std::max<int64_t>(1, query_total)));
+    DS_CHECK(ws.stage_out(&d_idf, idf64_by_col, (size_t)ENC_CODES));
+    DS_CHECK(ws.stage_out(&d_vocab, vocab_codes, (size_t)ENC_CODES));
+
+    int *d_present = nullptr, *d_df = nullptr, *d_bad = nullptr, *d_new_id = nullptr, *d_df_by_col = nullptr;
+    DS_CHECK(ws.alloc(&d_present, ENC_CODES + 1));
+    DS_CHECK(ws.alloc(&d_df, ENC_CODES));
+    DS_CHECK(ws.alloc(&d_bad, 1));
+    DS_CHECK(ws.alloc(&d_new_id, ENC_CODES + 1));
+    DS_CHECK(ws.alloc(&d_df_by_col, ENC_CODES));
+    DS_CUDA(cudaMemsetAsync(d_present, 0, (ENC_CODES + 1) * sizeof(int), stream));
+    DS_CUDA(cudaMemsetAsync(d_df, 0, ENC_CODES * sizeof(int), stream));
+    DS_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), stream));
+
+    int64_t truth_nnz = 0, query_nnz = 0;
+    DS_CHECK(encode_side(ws, d_tb, d_to, n_truth, d_tp, d_tc, d_present, d_df, d_bad, &truth_nnz));
+    DS_CHECK(encode_side(ws, d_qb, d_qo, n_queries, d_qp, d_qc, d_present, nullptr, d_bad, &query_nnz));
+
+    // canonical column ids = ranks of the present trigram codes
+    {
+        size_t temp_bytes = 0;
+        DS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, d_present, d_new_id, ENC_CODES + 1, stream));
+        unsigned char *temp = nullptr;
+        DS_CHECK(ws.alloc(&temp, temp_bytes));
+        DS_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, d_present, d_new_id, ENC_CODES + 1, stream));
+        g_kernel_launches.fetch_add(1);
+    }
+    int h_bad = 0, n_vocab = 0;
+    DS_CUDA(cudaMemcpyAsync(&n_vocab, d_new_id + ENC_CODES, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    DS_CUDA(cudaMemcpyAsync(&h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    DS_CUDA(cudaStreamSynchronize(stream));
+    if (h_bad) return fail(DS_ERR_BAD_ARG, "a title holds a character outside ' a-z0-9' (titles must be transform_title output)");
+    if (n_vocab > 65535) return fail(DS_ERR_UNSUPPORTED, "%d distinct trigrams exceed the 65535 u16 column ids", n_vocab);
+    if (truth_nnz > 0) {
+        k_remap<<<(unsigned)ceil_div(truth_nnz, 256), 256, 0, stream>>>(d_tc, truth_nnz, d_new_id);
+        DS_LAUNCHED("k_remap");
+    }
+    if (query_nnz > 0) {
+        k_remap<<<(unsigned)ceil_div(query_nnz, 256), 256, 0, stream>>>(d_qc, query_nnz, d_new_id);
+        DS_LAUNCHED("k_remap");
+    }
+    k_vocab<<<(unsigned)ceil_div(ENC_CODES, 256), 256, 0, stream>>>(d_present, d_new_id, d_df, d_vocab, d_df_by_col);
+    DS_LAUNCHED("k_vocab");
+
+    // idf on the host with the C library's log, exactly what CPython's math.log(N / df) evaluates (match_maker.py:139)
+    std::vector<int> h_df((size_t)std::max(1, n_vocab));
+    DS_CUDA(cudaMemcpyAsync(h_df.data(), d_df_by_col, (size_t)n_vocab * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    DS_CUDA(cudaStreamSynchronize(stream));
+    std::vector<double> h_idf((size_t)std::max(1, n_vocab));
+    double max_idf = 0.0;
+    bool any = false;
+    for (int c = 0; c < n_vocab; ++c) {
+        if (h_df[(size_t)c] > 0) {
+            h_idf[(size_t)c] = std::log((double)n_truth / (double)h_df[(size_t)c]);
+            max_idf = any ? std::max(max_idf, h_idf[(size_t)c]) : h_idf[(size_t)c];
+            any = true;
+        }
+    }
+    for (int c = 0; c < n_vocab; ++c)
+        if (h_df[(size_t)c] == 0) h_idf[(size_t)c] = max_idf;                    // query-only trigram (match_maker.py:151)
+    DS_CUDA(cudaMemcpyAsync(d_idf, h_idf.data(), (size_t)n_vocab * sizeof(double), cudaMemcpyHostToDevice, stream));
+    DS_CUDA(cudaStreamSynchronize(stream));
+    *out_n_vocab = n_vocab;
+    *out_truth_nnz = truth_nnz;
+    *out_query_nnz = query_nnz;
+    return ws.finish_outputs();
+}
+
+}  // extern "C"

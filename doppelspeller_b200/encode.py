@@ -77,3 +77,43 @@ def trigram_text(code):
     c0, rest = divmod(int(code), _BASE * _BASE)
     c1, c2 = divmod(rest, _BASE)
     return _ALPHABET[c0] + _ALPHABET[c1] + _ALPHABET[c2]
+
+
+def title_table(titles):
+    """Compact (bytes uint8[total], offsets int64[n+1]) table of ASCII titles (truncated to 255 like transform_title)."""
+    clipped = [t[:255] for t in titles]
+    lengths = np.fromiter((len(t) for t in clipped), dtype=np.int64, count=len(clipped))
+    offsets = np.zeros(len(clipped) + 1, dtype=np.int64)
+    np.cumsum(lengths, out=offsets[1:])
+    data = np.frombuffer(''.join(clipped).encode('latin-1', 'replace'), dtype=np.uint8)
+    return (np.array(data) if data.size else np.zeros(1, dtype=np.uint8)), offsets
+
+
+def encode_canonical_device(test_titles, truth_titles, device=0):
+    """`encode_canonical` on the GPU (csrc/ds_encode.cu): same outputs, as CUDA tensors that plug straight into
+    TruthIndex / MatchMaker.from_encoded without touching the host again."""
+    import ctypes
+
+    import torch
+
+    from . import _native as nat
+    dev = torch.device('cuda', device)
+    t_bytes, t_off = title_table(truth_titles)
+    q_bytes, q_off = title_table(test_titles)
+    to_dev = lambda x: torch.as_tensor(x).to(dev)   # noqa: E731
+    d_tb, d_to, d_qb, d_qo = to_dev(t_bytes), to_dev(t_off), to_dev(q_bytes), to_dev(q_off)
+    max_vocab = int(nat.lib.ds_encode_max_vocab())
+    t_ptr = torch.empty(len(truth_titles) + 1, dtype=torch.int64, device=dev)
+    q_ptr = torch.empty(len(test_titles) + 1, dtype=torch.int64, device=dev)
+    t_cols = torch.empty(max(1, int(t_off[-1])), dtype=torch.uint16, device=dev)
+    q_cols = torch.empty(max(1, int(q_off[-1])), dtype=torch.uint16, device=dev)
+    idf64 = torch.empty(max_vocab, dtype=torch.float64, device=dev)
+    vocab = torch.empty(max_vocab, dtype=torch.int32, device=dev)
+    n_vocab, t_nnz, q_nnz = ctypes.c_int32(0), ctypes.c_int64(0), ctypes.c_int64(0)
+    with torch.cuda.device(dev):
+        nat.check(nat.lib.ds_encode_trigrams(
+            nat.ptr(d_tb), nat.ptr(d_to), len(truth_titles), nat.ptr(d_qb), nat.ptr(d_qo), len(test_titles), nat.ptr(t_ptr),
+            nat.ptr(t_cols), nat.ptr(q_ptr), nat.ptr(q_cols), nat.ptr(idf64), nat.ptr(vocab), ctypes.byref(n_vocab),
+            ctypes.byref(t_nnz), ctypes.byref(q_nnz), device, torch.cuda.current_stream(dev).cuda_stream))
+    return dict(idf64=idf64[:n_vocab.value], t_ptr=t_ptr, t_cols=t_cols[:t_nnz.value], q_ptr=q_ptr, q_cols=q_cols[:q_nnz.value],
+                vocab_codes=vocab[:n_vocab.value], n_truth=len(truth_titles))

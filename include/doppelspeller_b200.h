@@ -87,6 +87,26 @@ int ds_index_destroy(ds_index *index);
 int ds_index_get_sums(const ds_index *index, float *out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * ds_encode_trigrams  -  the host half of MatchMaker.__init__ on the GPU: titles ->
+ * per-title trigram SETS (common.py:150-151) -> column ids -> document frequencies over the truth sets
+ * (common.py:145-147) -> idf = log(N / df), query-only trigrams weighted with the maximum idf
+ * (match_maker.py:95,135-153,180-181).  Column ids are CANONICAL (rank of the trigram in ' a..z0..9' code
+ * order), not the reference's PYTHONHASHSEED dependent set order; the arithmetic is the reference's.
+ *   *_bytes / *_offsets   compact title tables of transform_title output (characters ' a-z0-9' only)
+ *   t_row_ptr [n_truth+1], t_col_ids [capacity: total truth bytes]   truth CSR, ascending ids per title
+ *   q_row_ptr [n_queries+1], q_col_ids [capacity: total query bytes]
+ *   idf64_by_col, vocab_codes   [capacity: ds_encode_max_vocab() = 50,653]; vocab_codes[c] = c0*37^2+c1*37+c2
+ *   out_n_vocab / out_truth_nnz / out_query_nnz   host integers; the call synchronises `stream`.
+ * The outputs plug straight into ds_index_create / ds_topn (device pointers are used in place).
+ * ------------------------------------------------------------------------------------------------- */
+int32_t ds_encode_max_vocab(void);
+int ds_encode_trigrams(const uint8_t *truth_bytes, const int64_t *truth_offsets, int64_t n_truth,
+                       const uint8_t *query_bytes, const int64_t *query_offsets, int64_t n_queries,
+                       int64_t *t_row_ptr, uint16_t *t_col_ids, int64_t *q_row_ptr, uint16_t *q_col_ids,
+                       double *idf64_by_col, int32_t *vocab_codes, int32_t *out_n_vocab, int64_t *out_truth_nnz,
+                       int64_t *out_query_nnz, int device, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * ds_topn  -  replaces `[MatchMaker.get_closest_matches(row) for row in rows]`
  * (match_maker.py:192-203 = python sum :197 + fast_jaccard :16-50 + fast_arg_top_k :53-71), without
  * the title_id lookup of :190 (the binding maps rows to ids).

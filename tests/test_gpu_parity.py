@@ -261,3 +261,26 @@ def test_levenshtein_ratio_and_prematch_against_oracle(example_titles):
     got = predict.get_levenshtein_ratios(xs2, ys2)
     want = np.array([oracle.prematch_ratio(x, y) for x, y in zip(xs2, ys2)])
     assert np.array_equal(got, want)
+
+
+# ------------------------------------------------------------------ f1: GPU index encoding
+def test_gpu_trigram_encoder_matches_host_encoder():
+    import torch
+    from doppelspeller_b200 import encode, synthetic
+    from doppelspeller_b200.index import TruthIndex
+    truth = synthetic.generate_truth_titles(30000, seed=21) + synthetic.generate_long_titles(300, seed=22) + ['abc', 'aaaaaaa', 'ab ab ab ab']
+    test, _ = synthetic.generate_test_titles(truth, 3000, seed=23)
+    want = encode.encode_canonical(test, truth)
+    got = encode.encode_canonical_device(test, truth)
+    for key in ('t_ptr', 'q_ptr', 't_cols', 'q_cols', 'vocab_codes'):
+        assert np.array_equal(got[key].cpu().numpy(), want[key]), key
+    assert np.array_equal(got['idf64'].cpu().numpy().view(np.uint64), want['idf64'].view(np.uint64))     # same libm log as math.log
+    # device-resident encoding -> device-resident index -> candidates, no host copies in between
+    index = TruthIndex(got['t_ptr'], got['t_cols'], got['idf64'])
+    rows, count = index.topn(got['q_ptr'], got['q_cols'], 10)
+    host_index = TruthIndex(want['t_ptr'], want['t_cols'], want['idf64'])
+    want_rows, want_count = host_index.topn(want['q_ptr'], want['q_cols'], 10)
+    assert np.array_equal(rows.cpu().numpy(), want_rows)
+    with pytest.raises(Exception, match='outside'):
+        encode.encode_canonical_device(['bad\ttitle'], truth[:10])
+    del torch
