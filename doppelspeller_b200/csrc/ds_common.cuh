@@ -73,7 +73,8 @@ class Workspace {
     template <typename T>
     int alloc(T **out, size_t count) {
         void *p = nullptr;
-        size_t bytes = (count > 0 ? count : 1) * sizeof(T);
+        // rounded up to 16 bytes: the string kernels fetch whole aligned 32-bit words around a string
+        size_t bytes = (((count > 0 ? count : 1) * sizeof(T)) + 15) & ~(size_t)15;
         cudaError_t err = cudaMallocAsync(&p, bytes, stream_);
         if (err != cudaSuccess) {
             cudaGetLastError();

@@ -26,9 +26,12 @@ def shard_offsets(n_total, n_shards):
 
 
 def slice_truth_csr(t_row_ptr, t_col_ids, r0, r1):
+    """Rows [r0, r1) of a CSR as their own CSR (numpy arrays or torch tensors, host or device)."""
     ptr = t_row_ptr[r0:r1 + 1]
-    cols = t_col_ids[ptr[0]:ptr[-1]]
-    return np.ascontiguousarray(ptr - ptr[0]), np.ascontiguousarray(cols)
+    cols = t_col_ids[int(ptr[0]):int(ptr[-1])]
+    if isinstance(ptr, np.ndarray):
+        return np.ascontiguousarray(ptr - ptr[0]), np.ascontiguousarray(cols)
+    return (ptr - ptr[0]).contiguous(), cols.contiguous()
 
 
 def combine_rescans(per_shard_rows, per_shard_count, k):
@@ -58,8 +61,11 @@ class GpuShard:
         import torch
         self.index = index
         self.device = torch.device('cuda', index.device)
-        self.q_ptr = torch.as_tensor(np.ascontiguousarray(q_row_ptr, dtype=np.int64)).to(self.device)
-        self.q_cols = torch.as_tensor(np.ascontiguousarray(q_col_ids, dtype=np.uint16)).to(self.device)
+        if isinstance(q_row_ptr, np.ndarray):
+            q_row_ptr = torch.as_tensor(np.ascontiguousarray(q_row_ptr, dtype=np.int64))
+            q_col_ids = torch.as_tensor(np.ascontiguousarray(q_col_ids, dtype=np.uint16))
+        self.q_ptr = q_row_ptr.to(self.device, non_blocking=True).contiguous()
+        self.q_cols = q_col_ids.to(self.device, non_blocking=True).contiguous()
         self.mx_mode = mx_mode
         self.n_total = index.n_total
 
