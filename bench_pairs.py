@@ -114,6 +114,19 @@ def main():
     exact = (run_feats_first[:, :36] == want_feats[:, :36]) | (np.isnan(run_feats_first[:, :36]) & np.isnan(want_feats[:, :36]))
     with np.errstate(all='ignore'):
         close = np.isclose(run_feats_first[:, 36:], want_feats[:, 36:], rtol=1e-6, atol=0, equal_nan=True)
+    # CPU baseline: the C port of the reference (oracle/ds_oracle.c, OpenMP over pairs) on the same sample
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    oracle.indel_ratio_u8_batch(pa, pb, la_s, lb_s, n_threads=cores)
+    t_ratio = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    oracle.construct_features(la_s, lb_s, pa, pb, counts[idx_b[sel]], fe.SPACE_CODE, len(truth), n_threads=cores)
+    t_feat = time.perf_counter() - t0
+    line['cpu_baseline'] = {'kind': 'port', 'cores': cores, 'sample': f'the first {n} pairs of the batch',
+                            'indel_ratio_pairs_per_s': n / t_ratio, 'construct_features_pairs_per_s': n / t_feat}
     line['parity'] = {'sampled_pairs': int(n), 'ratio_mismatches': int((got_ratio != want_ratio).sum()),
                       'integer_feature_mismatches': int((~exact).sum()), 'float_feature_mismatches': int((~close).sum())}
     print(json.dumps(line), flush=True)

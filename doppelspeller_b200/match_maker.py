@@ -24,6 +24,7 @@ LOGGER = logging.getLogger(__name__)
 
 COLUMN_N_GRAMS = 'n_grams'      # constants.py:6
 COLUMN_TITLE_ID = 'title_id'    # constants.py:2
+COLUMN_TRANSFORMED_TITLE = 'transformed_title'   # constants.py:4
 TOO_FEW_ROWS_MESSAGE = 'top_matches.shape[0] != self.top_n'   # match_maker.py:189
 
 
@@ -49,12 +50,24 @@ class MatchMaker:
     :param device: CUDA device ordinal (default: torch's current device)
     :param mx_mode: how `max_intersection_possible` is summed (match_maker.py:197): the default follows
         CPython >= 3.12's compensated builtin sum(), DS_MX_NAIVE the plain sum of older interpreters
+    :param order: 'reference' (default) numbers the n-gram columns and sums each truth title's weights in the
+        reference's python-set iteration order - bit-identical to a reference MatchMaker of the same process;
+        'canonical' builds the whole index on the GPU from the `transformed_title` column (csrc/ds_encode.cu,
+        milliseconds instead of seconds): same arithmetic, hash-seed independent column order, so scores may
+        differ from one particular reference process in the last float bits (like two reference runs with
+        different PYTHONHASHSEED do)
     """
 
-    def __init__(self, data, truth_data, top_n, device=None, mx_mode=nat.DS_MX_PY312_COMPENSATED):
+    def __init__(self, data, truth_data, top_n, device=None, mx_mode=nat.DS_MX_PY312_COMPENSATED, order='reference'):
         self.top_n = top_n
         self.mx_mode = mx_mode
         LOGGER.info(f'[{self.__class__.__name__}] Loading pre-requisite data!')
+        if order == 'canonical':
+            self._init_canonical(data, truth_data, device)
+            LOGGER.info(f'[{self.__class__.__name__}] Loaded pre-requisite data!')
+            return
+        if order != 'reference':
+            raise ValueError("order must be 'reference' or 'canonical'")
         data_n_grams = list(data[COLUMN_N_GRAMS])
         truth_n_grams = list(truth_data[COLUMN_N_GRAMS])
 
@@ -94,6 +107,22 @@ class MatchMaker:
                           device, sums=sums)
         return self
 
+    def _init_canonical(self, data, truth_data, device):
+        import torch
+        from . import encode
+        if not torch.cuda.is_available():
+            raise nat.DoppelSpellerError(-2, 'no CUDA device available (doppelspeller_b200 has no CPU fallback)')
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.number_of_truth_titles = len(truth_data)
+        enc = encode.encode_canonical_device(list(data[COLUMN_TRANSFORMED_TITLE]), list(truth_data[COLUMN_TRANSFORMED_TITLE]),
+                                             device=self.device)
+        self.truth_data = truth_data.loc[:, [COLUMN_TITLE_ID]]
+        self.n_grams_decoding = None          # decoded lazily: vocab_codes holds the canonical trigram codes
+        self._vocab_codes = enc['vocab_codes']
+        self._index = TruthIndex(enc['t_ptr'], enc['t_cols'], enc['idf64'], device=self.device)
+        self._q_ptr, self._q_cols = enc['q_ptr'], enc['q_cols']
+        self._rows = self._count = self._flags = None
+
     def _init_device(self, idf64, t_ptr, t_cols, q_ptr, q_cols, device, sums=None):
         import torch
         if not torch.cuda.is_available():
@@ -114,6 +143,8 @@ class MatchMaker:
     def _compute_all(self):
         rows, count, _, flags = self._index.topn(self._q_ptr, self._q_cols, self.top_n, mx_mode=self.mx_mode,
                                                  with_details=True)
+        if hasattr(rows, 'cpu'):              # device-resident queries (canonical order): results to the host once
+            rows, count, flags = rows.cpu().numpy(), count.cpu().numpy(), flags.cpu().numpy()
         self._rows, self._count, self._flags = rows, count, flags
 
     def closest_rows(self):

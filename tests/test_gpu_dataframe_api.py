@@ -91,3 +91,22 @@ def test_prediction_fuzzy_prematch_cascade(example_titles, golden_matchmaker):
     m = m[~m['test_index'].isin(dup)]
     assert np.array_equal(kept, m.index.to_numpy())
     assert len(kept) > 0
+
+
+def test_matchmaker_canonical_order_gpu_index_build(example_titles, golden_matchmaker):
+    """order='canonical': index built on the GPU from the transformed titles; exact against the oracle on the
+    canonical encoding, and in practice the same candidate lists as the reference's own order."""
+    from doppelspeller_b200 import encode
+    from doppelspeller_b200.match_maker import MatchMaker
+    from oracle import oracle
+    n_q, k = 600, 10
+    truth = _frame(example_titles['truth_titles'], example_titles['truth_title_ids'])
+    data = _frame(example_titles['test_titles'][:n_q])
+    mm = MatchMaker(data, truth, k, order='canonical')
+    got = mm.get_closest_matches_batch()
+    enc = encode.encode_canonical(example_titles['test_titles'][:n_q], example_titles['truth_titles'])
+    want_rows, _, _ = oracle.topn(oracle_index_from_encoded(enc), k)
+    assert np.array_equal(got, example_titles['truth_title_ids'][want_rows])
+    assert mm.get_closest_matches(5) == example_titles['truth_title_ids'][want_rows[5]].tolist()
+    agree = (want_rows == golden_matchmaker['top10_rows'][:n_q]).all(axis=1).mean()
+    assert agree >= 0.995
