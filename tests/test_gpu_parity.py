@@ -284,3 +284,18 @@ def test_gpu_trigram_encoder_matches_host_encoder():
     with pytest.raises(Exception, match='outside'):
         encode.encode_canonical_device(['bad\ttitle'], truth[:10])
     del torch
+
+
+def test_large_vocabulary_uses_the_512_thread_scan():
+    """n_vocab near the 50,653 trigram maximum: the slot table alone is > 100 KB, so the scan runs as one
+    512-thread CTA per SM with the opt-in shared-memory carve-out."""
+    rng = np.random.default_rng(13)
+    n_vocab = 50600
+    hot = rng.choice(n_vocab, size=300, replace=False)           # a Zipf-like head so that scores collide and rank
+    def row(n):
+        cols = set(rng.choice(hot, size=n // 2, replace=False).tolist()) | set(rng.integers(0, n_vocab, size=n - n // 2).tolist())
+        return sorted(cols)
+    truth = [row(int(rng.integers(4, 30))) for _ in range(6000)]
+    queries = [row(int(rng.integers(3, 40))) for _ in range(150)] + [truth[i] for i in (5, 77, 4000)]
+    _check_against_oracle(_tiny_case(truth, queries, n_vocab), 10)
+    _check_against_oracle(_tiny_case(truth, queries, n_vocab), 100)
