@@ -399,6 +399,19 @@ def pair_kernels(truth, test, rows, device):
         peak, _ = measured_peak()
         out[name] = {'pairs_per_s': n / (ms / 1e3), 'pairs': n, 'ms': ms, 'algorithmic_bytes_per_pair': bytes_per_pair,
                      'hbm_frac': n * bytes_per_pair / (ms / 1e3) / 1e9 / peak}
+    # the whole hot path as one GPU-resident pass (north_star target: "100k test titles matched, nearest-n Jaccard +
+    # Levenshtein features, against 500k truth titles"): host title strings in, candidate rows + features out
+    from doppelspeller_b200.pipeline import CandidatePipeline
+    pipeline = CandidatePipeline(truth, device=device.index)
+    pipeline.run(test, k)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    p_rows, _, p_feats = pipeline.run(test, k)
+    torch.cuda.synchronize()
+    seconds = time.perf_counter() - t0
+    out['pipeline'] = {'what': 'title strings -> GPU index build (both sides) -> top-n candidates -> 66 features per candidate pair',
+                       'titles_per_s': n_q / seconds, 'ms': seconds * 1e3, 'candidate_pairs': int(p_feats.shape[0]),
+                       'rows_equal_step': bool(np.array_equal(p_rows.cpu().numpy(), rows))}
     return out
 
 

@@ -1,0 +1,58 @@
+"""The whole hot path as one GPU-resident pass: titles in, candidate rows + 66 features per candidate out.
+
+    encode (csrc/ds_encode.cu) -> top-n candidates (csrc/ds_topn.cu) -> features of every (title, candidate)
+    pair (csrc/ds_pairs.cu)
+
+This is what `Prediction.generate_test_predictions` does between the exact-match join and `model.predict`
+(/root/reference/doppelspeller/predict.py:286-219): MatchMaker(...) + get_closest_matches per row +
+construct_features on the title/candidate pairs - without the pandas glue and without materialising
+[P, 255] arrays.  Intermediate results never leave the device.
+"""
+from collections import Counter
+
+import numpy as np
+
+from . import encode
+from . import feature_engineering as fe
+from .index import TruthIndex
+
+
+def truth_word_counts(truth_titles):
+    """[n_truth, 15] uint32: document frequency of each of the first 15 words of every truth title
+    (common.get_words_counter common.py:140-142 + FeatureEngineering.get_truth_words_counts :309-319)."""
+    counter = Counter(w for t in truth_titles for w in set(t.split()))
+    counts = np.zeros((len(truth_titles), fe.NUMBER_OF_WORDS_FEATURES), dtype=np.uint32)
+    for i, t in enumerate(truth_titles):
+        ws = [counter[w] for w in t.split()[:fe.NUMBER_OF_WORDS_FEATURES]]
+        counts[i, :len(ws)] = ws
+    return counts
+
+
+class CandidatePipeline:
+    """Holds the truth side on the GPU (index, code table, word counts); `run(test_titles, top_n)` returns
+    (rows int64[Q, top_n] descending truth rows, features float32[Q * top_n, 66]) as CUDA tensors."""
+
+    def __init__(self, truth_titles, device=0):
+        import torch
+        self.device = torch.device('cuda', device)
+        self.truth_titles = truth_titles
+        codes, offsets = fe.encode_titles(truth_titles)
+        self.truth_codes = torch.as_tensor(codes).to(self.device)
+        self.truth_offsets = torch.as_tensor(offsets).to(self.device)
+        self.word_counts = torch.as_tensor(truth_word_counts(truth_titles).view(np.int32)).to(self.device)
+
+    def run(self, test_titles, top_n):
+        import torch
+        enc = encode.encode_canonical_device(test_titles, self.truth_titles, device=self.device.index)
+        index = TruthIndex(enc['t_ptr'], enc['t_cols'], enc['idf64'], device=self.device.index)
+        rows, count = index.topn(enc['q_ptr'], enc['q_cols'], top_n)
+        index.close()
+        codes, offsets = fe.encode_titles(test_titles)
+        test_codes = torch.as_tensor(codes).to(self.device)
+        test_offsets = torch.as_tensor(offsets).to(self.device)
+        n_q = len(test_titles)
+        title_index = torch.arange(n_q, device=self.device, dtype=torch.int32).repeat_interleave(top_n)
+        truth_index = rows.reshape(-1).clamp(min=0).to(torch.int32)
+        features = fe.construct_features_pairs((test_codes, test_offsets), (self.truth_codes, self.truth_offsets), self.word_counts,
+                                               title_index, truth_index, fe.SPACE_CODE, len(self.truth_titles))
+        return rows, count, features

@@ -110,3 +110,26 @@ def test_matchmaker_canonical_order_gpu_index_build(example_titles, golden_match
     assert mm.get_closest_matches(5) == example_titles['truth_title_ids'][want_rows[5]].tolist()
     agree = (want_rows == golden_matchmaker['top10_rows'][:n_q]).all(axis=1).mean()
     assert agree >= 0.995
+
+
+def test_candidate_pipeline_end_to_end(example_titles):
+    """titles -> GPU index build -> candidates -> 66 features per candidate, all device resident."""
+    from doppelspeller_b200 import encode
+    from doppelspeller_b200 import feature_engineering as fe
+    from doppelspeller_b200.pipeline import CandidatePipeline, truth_word_counts
+    from oracle import oracle
+    truth, test = example_titles['truth_titles'], example_titles['test_titles'][:300]
+    k = 10
+    rows, count, feats = CandidatePipeline(truth).run(test, k)
+    rows, feats = rows.cpu().numpy(), feats.cpu().numpy()
+    enc = encode.encode_canonical(test, truth)
+    want_rows, _, _ = oracle.topn(oracle_index_from_encoded(enc), k)
+    assert np.array_equal(rows, want_rows)
+    pairs_q, pairs_t = np.repeat(np.arange(len(test)), k), want_rows.reshape(-1)
+    la = np.array([len(test[q]) for q in pairs_q], np.uint8)
+    lb = np.array([len(truth[t]) for t in pairs_t], np.uint8)
+    a = np.vstack([fe.encode_title(test[q]) for q in pairs_q])
+    b = np.vstack([fe.encode_title(truth[t]) for t in pairs_t])
+    want = oracle.construct_features(la, lb, a, b, truth_word_counts(truth)[pairs_t], fe.SPACE_CODE, len(truth))
+    from tests.conftest import features_equal
+    assert features_equal(feats, want)
