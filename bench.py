@@ -403,7 +403,8 @@ def pair_kernels(truth, test, rows, device):
     # Levenshtein features, against 500k truth titles"): host title strings in, candidate rows + features out
     from doppelspeller_b200.pipeline import CandidatePipeline
     pipeline = CandidatePipeline(truth, device=device.index)
-    pipeline.run(test, k)
+    for _ in range(2):
+        pipeline.run(test, k)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     p_rows, _, p_feats = pipeline.run(test, k)

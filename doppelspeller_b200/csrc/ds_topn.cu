@@ -1173,13 +1173,13 @@ int ds_index_create(ds_index **out, int device, int64_t n_truth, int32_t n_vocab
         DS_CHECK(ws.stage_in(&d_cols, t_col_ids, (size_t)nnz));
         DS_CHECK(ws.stage_in(&d_w64_in, idf64_by_col, (size_t)n_vocab));
         DS_CHECK(ws.stage_in(&d_sums_in, sums_truth_f32, (size_t)n_truth));
-        DS_CUDA(cudaMalloc(&ix.w64, (size_t)n_vocab * 8));
-        DS_CUDA(cudaMalloc(&ix.w32, ((size_t)n_vocab + 1) * 4));
-        DS_CUDA(cudaMalloc(&ix.sums, (size_t)std::max<int64_t>(1, n_truth) * 4));
-        DS_CUDA(cudaMalloc(&ix.sums_pos, (size_t)std::max<int64_t>(1, n_truth) * 4));
-        DS_CUDA(cudaMalloc(&ix.perm, (size_t)std::max<int64_t>(1, n_truth) * 4));
+        DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.w64), (size_t)n_vocab * 8, stream));
+        DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.w32), ((size_t)n_vocab + 1) * 4, stream));
+        DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.sums), (size_t)std::max<int64_t>(1, n_truth) * 4, stream));
+        DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.sums_pos), (size_t)std::max<int64_t>(1, n_truth) * 4, stream));
+        DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.perm), (size_t)std::max<int64_t>(1, n_truth) * 4, stream));
         DS_CUDA(cudaMemcpyAsync(ix.perm, h_perm.data(), (size_t)n_truth * 4, cudaMemcpyHostToDevice, stream));
-        DS_CUDA(cudaMalloc(&ix.chunk_ptr, ((size_t)n_truth + 1) * 4));
+        DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.chunk_ptr), ((size_t)n_truth + 1) * 4, stream));
         DS_CUDA(cudaMemcpyAsync(ix.w64, d_w64_in, (size_t)n_vocab * 8, cudaMemcpyDeviceToDevice, stream));
         k_weights<<<(unsigned)ceil_div(n_vocab + 1, 256), 256, 0, stream>>>(ix.w64, ix.w32, n_vocab);
         DS_LAUNCHED("k_weights");
@@ -1204,7 +1204,7 @@ int ds_index_create(ds_index **out, int device, int64_t n_truth, int32_t n_vocab
         DS_CUDA(cudaStreamSynchronize(stream));
         if (ceil_div(nnz, 8) + n_truth >= ((int64_t)1 << 32)) return fail(DS_ERR_UNSUPPORTED, "index too large for 32-bit chunk offsets");
         ix.n_chunks = total_chunks;
-        DS_CUDA(cudaMalloc(&ix.chunks, std::max<size_t>(1, (size_t)total_chunks) * 16));
+        DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.chunks), std::max<size_t>(1, (size_t)total_chunks) * 16, stream));
         if (n_truth > 0) {
             k_row_pack<<<(unsigned)ceil_div(n_truth * 32, 256), 256, 0, stream>>>(d_ptr, d_cols, ix.chunk_ptr, n_truth, ix.perm,
                                                                                  (uint16_t)n_vocab, reinterpret_cast<uint16_t *>(ix.chunks));
@@ -1224,13 +1224,11 @@ int ds_index_create(ds_index **out, int device, int64_t n_truth, int32_t n_vocab
 int ds_index_destroy(ds_index *index) {
     if (index == nullptr) return DS_OK;
     DeviceGuard guard(index->ix.device);
-    cudaFree(index->ix.chunks);
-    cudaFree(index->ix.chunk_ptr);
-    cudaFree(index->ix.sums);
-    cudaFree(index->ix.sums_pos);
-    cudaFree(index->ix.perm);
-    cudaFree(index->ix.w32);
-    cudaFree(index->ix.w64);
+    // stream-ordered frees (the buffers come from the same pool as the per-call workspace): no device-wide
+    // synchronisation, unlike cudaFree
+    void *buffers[] = {index->ix.chunks, index->ix.chunk_ptr, index->ix.sums, index->ix.sums_pos, index->ix.perm, index->ix.w32, index->ix.w64};
+    for (void *b : buffers)
+        if (b != nullptr) cudaFreeAsync(b, nullptr);
     delete index;
     return DS_OK;
 }

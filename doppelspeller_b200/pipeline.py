@@ -40,10 +40,12 @@ class CandidatePipeline:
         self.truth_codes = torch.as_tensor(codes).to(self.device)
         self.truth_offsets = torch.as_tensor(offsets).to(self.device)
         self.word_counts = torch.as_tensor(truth_word_counts(truth_titles).view(np.int32)).to(self.device)
+        raw, raw_offsets = encode.title_table(truth_titles)            # ASCII bytes for the trigram encoder
+        self.truth_table = (torch.as_tensor(raw).to(self.device), torch.as_tensor(raw_offsets).to(self.device))
 
     def run(self, test_titles, top_n):
         import torch
-        enc = encode.encode_canonical_device(test_titles, self.truth_titles, device=self.device.index)
+        enc = encode.encode_canonical_device(test_titles, None, device=self.device.index, truth_table=self.truth_table)
         index = TruthIndex(enc['t_ptr'], enc['t_cols'], enc['idf64'], device=self.device.index)
         rows, count = index.topn(enc['q_ptr'], enc['q_cols'], top_n)
         index.close()
