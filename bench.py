@@ -425,7 +425,7 @@ def main():
     parser.add_argument('--queries', type=int, default=100000)
     parser.add_argument('--truth', type=int, default=500000)
     parser.add_argument('--top-n', type=int, default=10)
-    parser.add_argument('--cpu-sample', type=int, default=2000)
+    parser.add_argument('--cpu-sample', type=int, default=20000)
     parser.add_argument('--device-encode', action='store_true', help='build the index with the GPU encoder also at N=1')
     parser.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline / parity sample (profiling runs)')
     args = parser.parse_args()
