@@ -182,7 +182,7 @@ def workload_config(args, enc):
             'queries': args.queries, 'truth': args.truth, 'top_n': args.top_n, 'vocab': int(len(enc['idf64'])),
             'mean_trigrams_per_truth_title': mean_g,
             'l2': 'flushed between timed steps (256 MiB memset, untimed)',
-            'shard': 'truth rows, contiguous ranges, one per rank'}
+            'shard': getattr(args, 'layout', 'truth rows, contiguous ranges')}
 
 
 def run_ours(args):
@@ -202,56 +202,81 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=device)
     k = args.top_n
-    n_q, n_truth = args.queries, args.truth
-    offs = sharded.shard_offsets(n_truth, world)
+    n_q_total, n_truth = args.queries, args.truth
+    # 2-D layout: the truth rows are sharded over T ranks (exchange step: all_gather + merge inside each group of T
+    # ranks) and the queries are split over G = world / T such groups (independent, no collective between groups).
+    # Default T = 2 for N >= 2: the index is sharded no further than memory asks for, but the NCCL merge path is
+    # always exercised; --truth-shards N gives the fully truth-sharded layout of BASELINE configs[4].
+    n_shards = args.truth_shards if args.truth_shards > 0 else min(world, 2)
+    if world % n_shards != 0:
+        raise SystemExit(f'--truth-shards {n_shards} must divide the number of ranks {world}')
+    n_groups = world // n_shards
+    group_id, shard_id = rank // n_shards, rank % n_shards
+    subgroup = None
+    if world > 1:
+        for g in range(n_groups):
+            handle = dist.new_group(ranks=list(range(g * n_shards, (g + 1) * n_shards)))
+            if g == group_id:
+                subgroup = handle
+    q_offs = sharded.shard_offsets(n_q_total, n_groups)
+    q0, q1 = int(q_offs[group_id]), int(q_offs[group_id + 1])
+    n_q = q1 - q0
+    offs = sharded.shard_offsets(n_truth, n_shards)
+    rank_shard = shard_id
     if world > 1 or args.device_encode:
         # index build entirely on the GPU (csrc/ds_encode.cu): trigram sets, canonical column ids, df, idf
         from doppelspeller_b200 import encode, synthetic
         t0 = time.time()
         truth = synthetic.generate_truth_titles(n_truth)
-        test, _ = synthetic.generate_test_titles(truth, n_q)
+        test, _ = synthetic.generate_test_titles(truth, n_q_total)
         t1 = time.time()
         dev_enc = encode.encode_canonical_device(test, truth, device=local_rank)
         torch.cuda.synchronize()
         log(f'[bench] rank {rank}: titles generated in {t1 - t0:.1f}s, encoded on the GPU in {time.time() - t1:.2f}s '
             f'(vocab {dev_enc["idf64"].shape[0]})')
-        ptr, cols = sharded.slice_truth_csr(dev_enc['t_ptr'], dev_enc['t_cols'], int(offs[rank]), int(offs[rank + 1]))
+        ptr, cols = sharded.slice_truth_csr(dev_enc['t_ptr'], dev_enc['t_cols'], int(offs[rank_shard]), int(offs[rank_shard + 1]))
         idf64 = dev_enc['idf64']
         mean_g = float(dev_enc['t_cols'].shape[0]) / n_truth
         enc = {'q_ptr': dev_enc['q_ptr'].cpu().numpy(), 'q_cols': dev_enc['q_cols'].cpu().numpy(), 'idf64': idf64.cpu().numpy(),
                't_ptr': None, 'mean_g': mean_g}
         del truth
     else:
-        truth, test, enc = build_workload(n_q, n_truth)
-        ptr, cols = sharded.slice_truth_csr(enc['t_ptr'], enc['t_cols'], int(offs[rank]), int(offs[rank + 1]))
+        truth, test, enc = build_workload(n_q_total, n_truth)
+        ptr, cols = sharded.slice_truth_csr(enc['t_ptr'], enc['t_cols'], int(offs[rank_shard]), int(offs[rank_shard + 1]))
         idf64 = enc['idf64']
         enc['mean_g'] = float(np.diff(enc['t_ptr']).mean())
     t0 = time.time()
-    index = TruthIndex(ptr, cols, idf64, device=local_rank, row_offset=int(offs[rank]), n_total=n_truth)
+    index = TruthIndex(ptr, cols, idf64, device=local_rank, row_offset=int(offs[rank_shard]), n_total=n_truth)
     torch.cuda.synchronize()
-    log(f'[bench] rank {rank}: index of rows [{offs[rank]}, {offs[rank + 1]}) built in {time.time() - t0:.2f}s')
+    log(f'[bench] rank {rank}: truth rows [{offs[rank_shard]}, {offs[rank_shard + 1]}) x queries [{q0}, {q1}), index built in '
+        f'{time.time() - t0:.2f}s')
 
-    d_q_ptr = torch.as_tensor(enc['q_ptr']).to(device)
-    d_q_cols = torch.as_tensor(enc['q_cols']).to(device)
-    h_q_ptr = torch.as_tensor(enc['q_ptr']).pin_memory()
-    h_q_cols = torch.as_tensor(enc['q_cols']).pin_memory()
+    # this rank's query group
+    my_q_ptr = np.ascontiguousarray(enc['q_ptr'][q0:q1 + 1] - enc['q_ptr'][q0])
+    my_q_cols = np.ascontiguousarray(enc['q_cols'][enc['q_ptr'][q0]:enc['q_ptr'][q1]])
+    d_q_ptr = torch.as_tensor(my_q_ptr).to(device)
+    d_q_cols = torch.as_tensor(my_q_cols).to(device)
+    h_q_ptr = torch.as_tensor(my_q_ptr).pin_memory()
+    h_q_cols = torch.as_tensor(my_q_cols).pin_memory()
     h_rows = torch.empty((n_q, k), dtype=torch.int64).pin_memory()
     h_count = torch.empty((n_q,), dtype=torch.int32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
-    shard = sharded.GpuShard(index, enc['q_ptr'], enc['q_cols']) if world > 1 else None
+    shard = sharded.GpuShard(index, my_q_ptr, my_q_cols) if n_shards > 1 else None
 
+    args.layout = (f'{n_shards} truth shards (contiguous row ranges, all_gather + merge inside each group) x {n_groups} query groups'
+                   if world > 1 else 'single GPU')
     phase_ms = {} if os.environ.get('DS_PHASE_TIMING') else None
 
     def step_device():
-        if world > 1:
-            rows, count, _ = sharded.sharded_topn(shard, k, timings=phase_ms)
+        if n_shards > 1:
+            rows, count, _ = sharded.sharded_topn(shard, k, group=subgroup, timings=phase_ms)
             return rows, count
         return index.topn(d_q_ptr, d_q_cols, k)
 
     def step_e2e():
-        if world > 1:
-            sh = sharded.GpuShard(index, h_q_ptr.numpy(), h_q_cols.numpy())       # H2D of the queries
-            rows, count, _ = sharded.sharded_topn(sh, k)
+        if n_shards > 1:
+            sh = sharded.GpuShard(index, h_q_ptr, h_q_cols)                       # H2D of the queries
+            rows, count, _ = sharded.sharded_topn(sh, k, group=subgroup)
             h_rows.copy_(rows, non_blocking=True)                                 # D2H of the result
             h_count.copy_(count, non_blocking=True)
             torch.cuda.synchronize()
@@ -294,16 +319,17 @@ def run_ours(args):
     gpu_launches = nat.kernel_launches() - launches_before
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
-    value = n_q / (ms_per_step / 1e3)
+    value = n_q_total / (ms_per_step / 1e3)
     if phase_ms:
         log(f'[bench] rank {rank} phase ms per step: ' + ', '.join(f'{k_}={v / (args.steps + args.warmup):.2f}' for k_, v in phase_ms.items()))
 
     for _ in range(min(args.warmup, 2)):
         step_e2e()
     e2e_ms, (e_rows, e_count) = timed(step_e2e, args.steps)
-    e2e_value = n_q / (e2e_ms / args.steps / 1e3)
-    h2d = int(enc['q_ptr'].nbytes + enc['q_cols'].nbytes)
-    d2h = int(n_q * k * 8 + n_q * 4)
+    e2e_value = n_q_total / (e2e_ms / args.steps / 1e3)
+    # bytes copied per step summed over all ranks: every rank uploads its group's queries and reads back its rows
+    h2d = int(n_shards * (enc['q_ptr'].nbytes + enc['q_cols'].nbytes))
+    d2h = int(n_shards * (n_q_total * k * 8 + n_q_total * 4))
 
     if rank != 0:
         if world > 1:
@@ -336,7 +362,7 @@ def run_ours(args):
     if world == 1 and not args.no_cpu and enc.get('t_ptr') is not None:
         from oracle import oracle
         index_cpu = oracle_index(enc)
-        sample = cpu_sample(n_q, args.cpu_sample)
+        sample = cpu_sample(n_q_total, args.cpu_sample)
         time_cpu_port(index_cpu, sample[:64], k)
         seconds, want_rows, want_count = time_cpu_port(index_cpu, sample, k)
         line['cpu_baseline'] = {'value': len(sample) / seconds, 'unit': UNIT, 'cores': host_threads(), 'kind': 'port',
@@ -426,6 +452,8 @@ def main():
     parser.add_argument('--truth', type=int, default=500000)
     parser.add_argument('--top-n', type=int, default=10)
     parser.add_argument('--cpu-sample', type=int, default=20000)
+    parser.add_argument('--truth-shards', type=int, default=0,
+                        help='ranks the truth rows are sharded over (0 = auto: 2 when N >= 2); queries are split over N / T groups')
     parser.add_argument('--device-encode', action='store_true', help='build the index with the GPU encoder also at N=1')
     parser.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline / parity sample (profiling runs)')
     args = parser.parse_args()

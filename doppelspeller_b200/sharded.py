@@ -64,6 +64,7 @@ class GpuShard:
         if isinstance(q_row_ptr, np.ndarray):
             q_row_ptr = torch.as_tensor(np.ascontiguousarray(q_row_ptr, dtype=np.int64))
             q_col_ids = torch.as_tensor(np.ascontiguousarray(q_col_ids, dtype=np.uint16))
+        # pinned host tensors are copied asynchronously on the current stream (e2e path)
         self.q_ptr = q_row_ptr.to(self.device, non_blocking=True).contiguous()
         self.q_cols = q_col_ids.to(self.device, non_blocking=True).contiguous()
         self.mx_mode = mx_mode
