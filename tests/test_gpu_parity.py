@@ -299,3 +299,24 @@ def test_large_vocabulary_uses_the_512_thread_scan():
     queries = [row(int(rng.integers(3, 40))) for _ in range(150)] + [truth[i] for i in (5, 77, 4000)]
     _check_against_oracle(_tiny_case(truth, queries, n_vocab), 10)
     _check_against_oracle(_tiny_case(truth, queries, n_vocab), 100)
+
+
+def test_edge_degenerate_weights_and_empty_rows():
+    """All-zero idf (every trigram in every truth title: scores are 0/0 = NaN, nothing qualifies and the reference
+    raises), a single truth row, empty truth rows, duplicated truth rows."""
+    from oracle import oracle
+    # identical truth titles -> idf = log(N / N) = 0 everywhere -> NaN scores -> no row passes `array >= threshold`
+    same = _tiny_case([[0, 1, 2]] * 5, [[0, 1], [2], []], 3)
+    assert (same['idf64'] == 0).all()
+    rows, count, kth, flags = _match_maker(same, 2)._index.topn(same['q_ptr'], same['q_cols'], 2, with_details=True)
+    want_rows, want_count, _ = oracle.topn(oracle_index_from_encoded(same), 2)
+    assert np.array_equal(count, want_count) and (count == 0).all()
+    with pytest.raises(Exception, match=r'top_matches.shape\[0\] != self.top_n'):
+        _match_maker(same, 2).get_closest_matches(0)
+    # one truth row
+    _check_against_oracle(_tiny_case([[0, 1, 2]], [[0, 1], [5]], 8), 1)
+    # empty truth rows between real ones, duplicates, a query equal to a truth row
+    truth = [[], [0, 1, 2], [], [3, 4], [0, 1, 2], [], [5], [0, 1, 2], []] * 30
+    queries = [[0, 1, 2], [3], [], [5, 6], [0, 4, 5]]
+    for k in (1, 3, 10, 100):
+        _check_against_oracle(_tiny_case(truth, queries, 8), k)
