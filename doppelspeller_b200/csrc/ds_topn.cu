@@ -11,7 +11,7 @@
 //            in descending row order.
 //   mx       doppelspeller/match_maker.py:197     python sum() over the ascending column ids
 //
-// Design (B200): the truth rows live in HBM as 16-byte chunks of eight ascending u16 column ids
+// Design (B200): the truth rows live in HBM as 8-byte chunks of four ascending u16 column ids
 // (sentinel padded); a CTA owns a tile of up to 32 queries whose columns are scattered once into a
 // shared-memory direct map  column id -> slot -> (32-bit query mask, idf32)  and then streams truth
 // rows, one row per thread, with 32 register accumulators.  Adding the row's columns in ascending
@@ -41,6 +41,11 @@ struct ScanProfile {
 static ScanProfile g_profile;
 
 constexpr int TQ = 32;              // queries per tile (one bit each in the slot mask)
+constexpr int CHUNK_COLS = 4;       // u16 column ids per chunk: 4 -> one LDG.64 per chunk (7.7 % sentinel padding at the
+                                    // example length distribution; 8 -> LDG.128, 17 % padding)
+typedef uint2 chunk_t;
+static_assert(sizeof(chunk_t) == CHUNK_COLS * 2, "chunk type and CHUNK_COLS disagree");
+__device__ __forceinline__ chunk_t zero_chunk() { return make_uint2(0, 0); }
 constexpr int MAX_SLOTS = 2048;     // slot 0 = "column not in this tile"
 constexpr int CAND_CAP_MAX = 1024;  // per query candidate buffer (per scan launch): clamp(8 * k, 256, 1024)
 constexpr int DENSE_ROWS = 256;     // rows of the first (dense, threshold seeding) chunk
@@ -62,7 +67,7 @@ struct Index {
     // by their chunk count, so the 32 rows of a warp stream (nearly) the same number of chunks.  Everything
     // indexed by "position" below uses that order; perm[position] is the shard-local original row.
     int32_t *perm = nullptr;        // [n_truth] position -> original row
-    uint4 *chunks = nullptr;        // [n_chunks] eight ascending u16 column ids, sentinel = n_vocab
+    chunk_t *chunks = nullptr;      // [n_chunks] CHUNK_COLS ascending u16 column ids, sentinel = n_vocab
     uint32_t *chunk_ptr = nullptr;  // [n_truth + 1] by position
     float *sums_pos = nullptr;      // [n_truth] sums_matrix_truth by position
     float *sums = nullptr;          // [n_truth] sums_matrix_truth by original row
@@ -124,7 +129,7 @@ __global__ void k_row_prepare(const int64_t *__restrict__ row_ptr, const uint16_
     if (pos >= n_rows) return;
     const int64_t r = perm[pos];
     int64_t p0 = row_ptr[r], p1 = row_ptr[r + 1];
-    n_chunks[pos] = (uint32_t)((p1 - p0 + 7) / 8);
+    n_chunks[pos] = (uint32_t)((p1 - p0 + CHUNK_COLS - 1) / CHUNK_COLS);
     float acc = 0.0f;
     if (compute_sums) {
         for (int64_t p = p0; p < p1; ++p) acc = __fadd_rn(acc, w32[min((int)cols[p], n_vocab)]);
@@ -145,8 +150,8 @@ __global__ void k_row_pack(const int64_t *__restrict__ row_ptr, const uint16_t *
     const int64_t r = perm[pos];
     int64_t p0 = row_ptr[r];
     int g = (int)(row_ptr[r + 1] - p0);
-    uint16_t *dst = out + (size_t)chunk_ptr[pos] * 8;
-    int padded = (int)(chunk_ptr[pos + 1] - chunk_ptr[pos]) * 8;
+    uint16_t *dst = out + (size_t)chunk_ptr[pos] * CHUNK_COLS;
+    int padded = (int)(chunk_ptr[pos + 1] - chunk_ptr[pos]) * CHUNK_COLS;
     for (int i = lane; i < padded; i += 32) {
         if (i >= g) dst[i] = sentinel;
     }
@@ -213,7 +218,7 @@ __global__ void k_query_prepare(const int64_t *__restrict__ q_ptr, const uint16_
 // K1 scan kernel
 // ---------------------------------------------------------------------------------------------------
 struct ScanParams {
-    const uint4 *chunks;
+    const chunk_t *chunks;
     const uint32_t *chunk_ptr;
     const float *sums;          // by position
     const float *w32;
@@ -310,7 +315,7 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) k_scan(ScanParams p) {
     int row = cta_r0 + tid;
     uint32_t c0 = 0, c1 = 0;
     float sum_t = 0.0f;
-    uint4 ch = make_uint4(0, 0, 0, 0);
+    chunk_t ch = zero_chunk();
     if (row < cta_r1) {
         c0 = p.chunk_ptr[row];
         c1 = p.chunk_ptr[row + 1];
@@ -331,18 +336,18 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) k_scan(ScanParams p) {
         for (int j = 0; j < TQ; ++j) sc[j] = 0.0f;
 #pragma unroll 1
         for (uint32_t c = c0; c < c1; ++c) {
-            uint4 next_ch = make_uint4(0, 0, 0, 0);
+            chunk_t next_ch = zero_chunk();
             if (c + 1 < c1) next_ch = __ldg(p.chunks + c + 1);
             else if (n0 < n1) next_ch = __ldg(p.chunks + n0);
-            const uint32_t words[4] = {ch.x, ch.y, ch.z, ch.w};
-            uint2 ent[8];
+            const uint32_t words[CHUNK_COLS / 2] = {ch.x, ch.y};
+            uint2 ent[CHUNK_COLS];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < CHUNK_COLS; ++i) {
                 uint32_t col = (words[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
                 ent[i] = entries[slot16[col]];
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) accumulate_column(sc, ent[i].x, __uint_as_float(ent[i].y));
+            for (int i = 0; i < CHUNK_COLS; ++i) accumulate_column(sc, ent[i].x, __uint_as_float(ent[i].y));
             ch = next_ch;
         }
         if (c0 == c1 && n0 < n1) ch = __ldg(p.chunks + n0);   // empty row: nothing was prefetched above
@@ -949,7 +954,7 @@ static int run_pipeline(Workspace &call_ws, const Index &ix, const QuerySet &qs,
         int64_t r1;
         if (dense) r1 = std::min<int64_t>(n, r0 + dense_rows);
         else if (mode == MODE_ROW) r1 = n;  // the threshold is fixed: one pass over all rows
-        else r1 = std::min<int64_t>(n, std::max<int64_t>(2 * r0, r0 + dense_rows));
+        else r1 = std::min<int64_t>(n, std::max<int64_t>(2 * r0, r0 + dense_rows));   // doubling sweep: thresholds tighten early (x4 overflows the candidate buffers)
         sp.r0 = (int)r0;
         sp.r1 = (int)r1;
         sp.dense = dense ? d_dense : nullptr;
@@ -1142,13 +1147,13 @@ int ds_index_create(ds_index **out, int device, int64_t n_truth, int32_t n_vocab
             for (int64_t r = b0; r < b1; ++r) {
                 const int64_t g = h_ptr[(size_t)r + 1] - h_ptr[(size_t)r];
                 if (g < 0) return fail(DS_ERR_BAD_ARG, "t_row_ptr is decreasing at row %lld", (long long)r);
-                max_chunks = std::max(max_chunks, (g + 7) / 8);
+                max_chunks = std::max(max_chunks, (g + CHUNK_COLS - 1) / CHUNK_COLS);
             }
             bucket_start.assign((size_t)max_chunks + 2, 0);
-            for (int64_t r = b0; r < b1; ++r) bucket_start[(size_t)((h_ptr[(size_t)r + 1] - h_ptr[(size_t)r] + 7) / 8) + 1]++;
+            for (int64_t r = b0; r < b1; ++r) bucket_start[(size_t)((h_ptr[(size_t)r + 1] - h_ptr[(size_t)r] + CHUNK_COLS - 1) / CHUNK_COLS) + 1]++;
             for (size_t c = 1; c < bucket_start.size(); ++c) bucket_start[c] += bucket_start[c - 1];
             for (int64_t r = b0; r < b1; ++r) {
-                const size_t c = (size_t)((h_ptr[(size_t)r + 1] - h_ptr[(size_t)r] + 7) / 8);
+                const size_t c = (size_t)((h_ptr[(size_t)r + 1] - h_ptr[(size_t)r] + CHUNK_COLS - 1) / CHUNK_COLS);
                 h_perm[(size_t)(b0 + bucket_start[c]++)] = (int32_t)r;
             }
         }
@@ -1202,9 +1207,9 @@ int ds_index_create(ds_index **out, int device, int64_t n_truth, int32_t n_vocab
         uint32_t total_chunks = 0;
         DS_CUDA(cudaMemcpyAsync(&total_chunks, ix.chunk_ptr + n_truth, 4, cudaMemcpyDeviceToHost, stream));
         DS_CUDA(cudaStreamSynchronize(stream));
-        if (ceil_div(nnz, 8) + n_truth >= ((int64_t)1 << 32)) return fail(DS_ERR_UNSUPPORTED, "index too large for 32-bit chunk offsets");
+        if (ceil_div(nnz, CHUNK_COLS) + n_truth >= ((int64_t)1 << 32)) return fail(DS_ERR_UNSUPPORTED, "index too large for 32-bit chunk offsets");
         ix.n_chunks = total_chunks;
-        DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.chunks), std::max<size_t>(1, (size_t)total_chunks) * 16, stream));
+        DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.chunks), std::max<size_t>(1, (size_t)total_chunks) * sizeof(chunk_t), stream));
         if (n_truth > 0) {
             k_row_pack<<<(unsigned)ceil_div(n_truth * 32, 256), 256, 0, stream>>>(d_ptr, d_cols, ix.chunk_ptr, n_truth, ix.perm,
                                                                                  (uint16_t)n_vocab, reinterpret_cast<uint16_t *>(ix.chunks));
