@@ -320,3 +320,40 @@ def test_edge_degenerate_weights_and_empty_rows():
     queries = [[0, 1, 2], [3], [], [5, 6], [0, 4, 5]]
     for k in (1, 3, 10, 100):
         _check_against_oracle(_tiny_case(truth, queries, 8), k)
+
+
+def test_candidate_buffer_overflow_falls_back_to_bounded_mode():
+    """5,000 identical truth rows late in the DB tie at the top of a query: the per-launch candidate buffer and
+    the rescan buffer both overflow, so the bounded-memory (dense, fixed-size chunk) passes must take over."""
+    rng = np.random.default_rng(17)
+    n_vocab = 400
+    truth = [sorted(rng.choice(n_vocab, size=int(rng.integers(3, 12)), replace=False).tolist()) for _ in range(20000)]
+    hot = [5, 17, 33, 90, 200, 201]
+    for r in range(9000, 14000):
+        truth[r] = hot
+    queries = [hot, hot[:4], sorted(rng.choice(n_vocab, size=8, replace=False).tolist()), [5, 17, 350]]
+    for k in (10, 100):
+        rows, count, flags = _check_against_oracle(_tiny_case(truth, queries, n_vocab), k)
+        assert rows[0].tolist() == list(range(13999, 13999 - k, -1))
+        assert flags[0] & 1
+
+
+def test_randomised_shapes_against_oracle():
+    """Fuzz over DB size, batch size, top_n, vocabulary and duplication."""
+    rng = np.random.default_rng(23)
+    for trial in range(24):
+        n_truth = int(rng.choice([1, 2, 7, 40, 300, 1500, 6000]))
+        n_vocab = int(rng.choice([3, 12, 60, 500, 5000]))
+        n_q = int(rng.integers(1, 120))
+        k = int(rng.choice([1, 2, 5, 10, 37, 100, 250]))
+        def row(max_len):
+            n = int(rng.integers(0, min(max_len, n_vocab) + 1))
+            return sorted(rng.choice(n_vocab, size=n, replace=False).tolist())
+        truth = [row(30) for _ in range(n_truth)]
+        if trial % 3 == 0 and n_truth > 4:                      # duplicates
+            for r in rng.integers(0, n_truth, n_truth // 2):
+                truth[int(r)] = truth[0]
+        if not any(truth):
+            truth[0] = [0]
+        queries = [row(60) for _ in range(n_q)]
+        _check_against_oracle(_tiny_case(truth, queries, n_vocab), k)
