@@ -133,6 +133,19 @@ def measured_peak():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def committed_issue_utilisation():
+    """Issue-slot utilisation of k_scan from the committed ncu capture (the real limiter of the kernel)."""
+    import csv
+    path = os.path.join(ROOT, 'profiles', 'r1_k_scan_metrics.csv')
+    if not os.path.exists(path):
+        return None
+    for row in csv.reader(open(path)):
+        if row and row[0] == 'sm__inst_issued.avg.pct_of_peak_sustained_active':
+            values = [float(v) for v in row[2:] if v]
+            return sum(values) / len(values) / 100.0 if values else None
+    return None
+
+
 def committed_traffic():
     """DRAM bytes per k_scan launch from the committed ncu capture, if one has been summarised."""
     path = os.path.join(ROOT, 'profiles', 'k_scan_traffic.json')
@@ -344,6 +357,7 @@ def run_ours(args):
                 'traffic': committed_traffic(), 'peak_source': peak_source, 'algorithmic_bytes_per_pair': bytes_per_pair,
                 'launches': int(scan_launches), 'avg_launch_ms': scan_ms / max(1, scan_launches),
                 'kernel_share_of_step': scan_ms / total_ms if total_ms > 0 else None,
+                'issue_slot_utilisation_ncu': committed_issue_utilisation(),
                 'note': 'reporting convention of SURVEY.md 8(d): the truth index is L2 resident and reused by every '
                         'query tile, so frac > 1 is expected; the kernel is issue bound (see profiles/)'}
 
