@@ -9,6 +9,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include "../../include/doppelspeller_b200.h"
@@ -171,5 +174,22 @@ class DeviceGuard {
 };
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Opt-in dynamic shared memory above 48 KB is a per-device attribute of a kernel: remembers, per kernel and
+// per device, the largest size already granted.
+inline int ensure_dynamic_smem(const void *kernel, size_t bytes) {
+    static std::mutex lock;
+    static std::map<std::pair<int, const void *>, size_t> granted;
+    if (bytes <= 48 * 1024) return DS_OK;
+    int device = 0;
+    DS_CUDA(cudaGetDevice(&device));
+    std::lock_guard<std::mutex> guard(lock);
+    size_t &have = granted[std::make_pair(device, kernel)];
+    if (bytes > have) {
+        DS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        have = bytes;
+    }
+    return DS_OK;
+}
 
 }  // namespace ds

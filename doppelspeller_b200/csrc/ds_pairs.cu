@@ -619,11 +619,7 @@ template <typename W, int MAXLEN, int BLOCK, int MODE>
 static int launch_indel_class(const PairSource &src, const int32_t *list, int64_t n, const K2Out &out, cudaStream_t stream) {
     if (n <= 0) return DS_OK;
     const size_t smem = sizeof(K2Smem<W, MAXLEN, BLOCK>);
-    static bool attr_done = false;
-    if (!attr_done) {
-        DS_CUDA((cudaFuncSetAttribute(k_indel_pairs<W, MAXLEN, BLOCK, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
-        attr_done = true;
-    }
+    DS_CHECK((ensure_dynamic_smem(reinterpret_cast<const void *>(&k_indel_pairs<W, MAXLEN, BLOCK, MODE>), smem)));
     k_indel_pairs<W, MAXLEN, BLOCK, MODE><<<(unsigned)ceil_div(n, BLOCK), BLOCK, smem, stream>>>(src, list, n, out);
     DS_LAUNCHED("k_indel_pairs");
     return DS_OK;

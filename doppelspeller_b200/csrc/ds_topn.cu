@@ -810,18 +810,10 @@ static int launch_scan(const Index &ix, cudaStream_t stream, ScanParams sp, int 
             DS_CUDA(cudaEventRecord(ev_start, stream));
         }
         if (big) {
-            static bool attr_done = false;
-            if (!attr_done) {
-                DS_CUDA(cudaFuncSetAttribute(k_scan<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                attr_done = true;
-            }
+            DS_CHECK(ensure_dynamic_smem(reinterpret_cast<const void *>(&k_scan<512>), smem));
             k_scan<512><<<grid, 512, smem, stream>>>(part);
         } else {
-            static bool attr_done = false;
-            if (!attr_done) {
-                DS_CUDA(cudaFuncSetAttribute(k_scan<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-                attr_done = true;
-            }
+            DS_CHECK(ensure_dynamic_smem(reinterpret_cast<const void *>(&k_scan<256>), smem));
             k_scan<256><<<grid, 256, smem, stream>>>(part);
         }
         DS_LAUNCHED("k_scan");
@@ -839,11 +831,7 @@ static int launch_select(cudaStream_t stream, SelectParams sp) {
     int items = std::max(sp.cap, sp.dense_rows) + sp.m;
     sp.max_items = items;
     size_t smem = (size_t)4 * items * 12;
-    static size_t attr_bytes = 0;
-    if (smem > 48 * 1024 && smem > attr_bytes) {
-        DS_CUDA(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_bytes = smem;
-    }
+    DS_CHECK(ensure_dynamic_smem(reinterpret_cast<const void *>(&k_select), smem));
     k_select<<<(unsigned)ceil_div(sp.n_batch, 4), 128, smem, stream>>>(sp);
     DS_LAUNCHED("k_select");
     return DS_OK;
