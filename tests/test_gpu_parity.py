@@ -4,7 +4,7 @@ relative for the float32 idf / rank features (north_star tolerance)."""
 import numpy as np
 import pytest
 
-from tests.conftest import features_equal, oracle_index_from_encoded, oracle_index_from_golden
+from tests.conftest import features_equal, oracle_index_from_encoded
 
 pytestmark = pytest.mark.gpu
 
@@ -87,12 +87,10 @@ def _check_against_oracle(enc, k):
 def test_edge_massive_ties_and_dropped_argmax():
     # 400 identical truth rows tie at the k-th place: more than the retained list can hold -> exact rescan,
     # and (like the reference) the k HIGHEST rows win even though an earlier row scores higher
-    rng = np.random.default_rng(7)
     truth = [[0, 1, 2, 3]] + [[0, 1, 5 + i % 3] for i in range(30)] + [[0, 1, 9]] * 400 + [[20 + i, 21 + i] for i in range(50)]
     queries = [[0, 1, 2, 3], [0, 1, 9], [0, 1], [0, 1, 9, 30, 31], [40, 41, 42]]
     rows, count, flags = _check_against_oracle(_tiny_case(truth, queries, 80), 10)
     assert (flags & 1).any()
-    del rng
 
 
 def test_edge_fewer_than_k_positives_returns_last_rows():
@@ -265,7 +263,6 @@ def test_levenshtein_ratio_and_prematch_against_oracle(example_titles):
 
 # ------------------------------------------------------------------ f1: GPU index encoding
 def test_gpu_trigram_encoder_matches_host_encoder():
-    import torch
     from doppelspeller_b200 import encode, synthetic
     from doppelspeller_b200.index import TruthIndex
     truth = synthetic.generate_truth_titles(30000, seed=21) + synthetic.generate_long_titles(300, seed=22) + ['abc', 'aaaaaaa', 'ab ab ab ab']
@@ -283,7 +280,6 @@ def test_gpu_trigram_encoder_matches_host_encoder():
     assert np.array_equal(rows.cpu().numpy(), want_rows)
     with pytest.raises(Exception, match='outside'):
         encode.encode_canonical_device(['bad\ttitle'], truth[:10])
-    del torch
 
 
 def test_large_vocabulary_uses_the_512_thread_scan():
