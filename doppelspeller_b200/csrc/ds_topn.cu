@@ -496,14 +496,31 @@ __global__ void __launch_bounds__(128) k_select(SelectParams p) {
     }
     const int total = n + n_old;
     __syncwarp();
+    // Final rank of every element in the union.  The old list [n, n + n_old) is already sorted in this mode's
+    // order, so: a candidate ranks behind the candidates that beat it plus a binary search into the old list; an
+    // old element keeps its position plus the candidates that beat it.  (n^2 + n * n_old instead of (n + n_old)^2.)
+    const double *o_score = s_score + n;
+    const int32_t *o_row = s_row + n;
     for (int i = lane; i < total; i += 32) {
         const double si = s_score[i];
         const int ri = s_row[i];
         int rank = 0;
         if (by_row) {
-            for (int j = 0; j < total; ++j) rank += s_row[j] > ri;
+            for (int j = 0; j < n; ++j) rank += s_row[j] > ri;
         } else {
-            for (int j = 0; j < total; ++j) rank += better(s_score[j], s_row[j], si, ri);
+            for (int j = 0; j < n; ++j) rank += better(s_score[j], s_row[j], si, ri);
+        }
+        if (i < n) {
+            int lo = 0, hi = n_old;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const bool ahead = by_row ? (o_row[mid] > ri) : better(o_score[mid], o_row[mid], si, ri);
+                if (ahead) lo = mid + 1;
+                else hi = mid;
+            }
+            rank += lo;
+        } else {
+            rank += i - n;
         }
         if (rank < p.m) {
             p.ret_score[(size_t)b * p.m + rank] = si;
