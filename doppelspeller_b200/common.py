@@ -21,7 +21,7 @@ def _string_table(texts):
     data = np.frombuffer(b''.join(encoded), dtype=np.uint8)
     if data.size == 0:
         data = np.zeros(1, dtype=np.uint8)
-    return np.ascontiguousarray(data), offsets
+    return np.array(data), offsets      # a writable copy (np.frombuffer views are read-only)
 
 
 def levenshtein_ratio_batch(texts, texts_to_match):

@@ -46,6 +46,60 @@ def get_levenshtein_ratios(titles, matches, threshold=LEVENSHTEIN_RATIO_THRESHOL
     return out
 
 
+class PrematchTables:
+    """Device-resident string tables of one title collection for the indexed pre-match: the raw titles and
+    their token-sorted forms (`' '.join(sorted(title.split()))`, common.py:166 - sorted once per TITLE, not once
+    per pair like the reference's per-pair lambda does)."""
+
+    def __init__(self, titles, device=0):
+        import torch
+
+        from .common import _string_table, _token_sort
+        self.device = torch.device('cuda', device)
+        raw, raw_off = _string_table(titles)
+        srt, srt_off = _string_table([_token_sort(t) for t in titles])
+        to_dev = lambda x: torch.as_tensor(x).to(self.device)   # noqa: E731
+        self.raw, self.raw_off, self.sorted, self.sorted_off = to_dev(raw), to_dev(raw_off), to_dev(srt), to_dev(srt_off)
+        self.lengths = to_dev(np.diff(raw_off))
+        self.n = len(titles)
+
+
+def _ratio_pairs(bytes_a, off_a, n_a, bytes_b, off_b, n_b, idx_a, idx_b):
+    import torch
+
+    from . import _native as nat
+    n = int(idx_a.shape[0])
+    out = torch.empty(n, dtype=torch.int32, device=idx_a.device)
+    if n:
+        nat.check(nat.lib.ds_levenshtein_ratio_pairs(nat.ptr(bytes_a), nat.ptr(off_a), n_a, nat.ptr(bytes_b), nat.ptr(off_b), n_b,
+                                                     nat.ptr(idx_a), nat.ptr(idx_b), n, nat.ptr(out), nat.current_stream()))
+    return out
+
+
+def get_levenshtein_ratios_indexed(tables_a, tables_b, idx_a, idx_b, threshold=LEVENSHTEIN_RATIO_THRESHOLD):
+    """Prediction._get_levenshtein_ratio (predict.py:140-156) for the pairs (tables_a[idx_a[p]], tables_b[idx_b[p]]),
+    entirely on the GPU: float64 length pre-filter, levenshtein_ratio of the survivors, token-sort ratio of
+    those at or below the threshold.  idx_* are int32 CUDA tensors; returns an int32 CUDA tensor."""
+    import torch
+    idx_a, idx_b = idx_a.to(torch.int32).contiguous(), idx_b.to(torch.int32).contiguous()
+    out = torch.zeros(idx_a.shape[0], dtype=torch.int32, device=idx_a.device)
+    la = tables_a.lengths[idx_a.long()].to(torch.float64)
+    lb = tables_b.lengths[idx_b.long()].to(torch.float64)
+    total = la + lb
+    deletion = ((total - (la - lb).abs()) / total) * 100                       # predict.py:140-145, float64, same association
+    keep = torch.nonzero(~(deletion < threshold)).flatten()                    # NaN (0 / 0) is not < threshold, like python
+    if keep.numel() == 0:
+        return out
+    ka, kb = idx_a[keep].contiguous(), idx_b[keep].contiguous()
+    ratios = _ratio_pairs(tables_a.raw, tables_a.raw_off, tables_a.n, tables_b.raw, tables_b.raw_off, tables_b.n, ka, kb)
+    again = torch.nonzero(ratios <= threshold).flatten()
+    if again.numel():
+        ratios[again] = _ratio_pairs(tables_a.sorted, tables_a.sorted_off, tables_a.n, tables_b.sorted, tables_b.sorted_off,
+                                     tables_b.n, ka[again].contiguous(), kb[again].contiguous())
+    out[keep] = ratios
+    return out
+
+
 def select_close_matches(test_index, ratios, threshold=LEVENSHTEIN_RATIO_THRESHOLD):
     """predict.py:158-176: positions of the pairs kept as "very close" matches: ratio > threshold, equal to
     the maximum of their test_index, and that maximum attained exactly once."""

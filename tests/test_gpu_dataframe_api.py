@@ -133,3 +133,23 @@ def test_candidate_pipeline_end_to_end(example_titles):
     want = oracle.construct_features(la, lb, a, b, truth_word_counts(truth)[pairs_t], fe.SPACE_CODE, len(truth))
     from tests.conftest import features_equal
     assert features_equal(feats, want)
+
+
+def test_indexed_prematch_matches_per_pair_form(example_titles, golden_matchmaker):
+    """The table + index form of the fuzzy pre-match (token sort once per title, everything on the GPU) against
+    the per-pair form and the oracle."""
+    import torch
+    from doppelspeller_b200 import predict
+    from oracle import oracle
+    n_q, k = 400, 100
+    truth, test = example_titles['truth_titles'], example_titles['test_titles'][:n_q]
+    rows = golden_matchmaker['top100_rows'][:n_q]
+    idx_a = torch.arange(n_q, dtype=torch.int32).repeat_interleave(k).cuda()
+    idx_b = torch.as_tensor(rows.reshape(-1).astype(np.int32)).cuda()
+    got = predict.get_levenshtein_ratios_indexed(predict.PrematchTables(test), predict.PrematchTables(truth), idx_a, idx_b).cpu().numpy()
+    titles = [test[q] for q in range(n_q) for _ in range(k)]
+    matches = [truth[t] for t in rows.reshape(-1)]
+    assert np.array_equal(got, predict.get_levenshtein_ratios(titles, matches))
+    sample = np.random.default_rng(0).choice(len(titles), 3000, replace=False)
+    assert np.array_equal(got[sample], np.array([oracle.prematch_ratio(titles[i], matches[i]) for i in sample]))
+    assert (got > 94).sum() > 0 and (got == 0).sum() > 0
