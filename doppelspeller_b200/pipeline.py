@@ -42,8 +42,12 @@ class CandidatePipeline:
         self.word_counts = torch.as_tensor(truth_word_counts(truth_titles).view(np.int32)).to(self.device)
         raw, raw_offsets = encode.title_table(truth_titles)            # ASCII bytes for the trigram encoder
         self.truth_table = (torch.as_tensor(raw).to(self.device), torch.as_tensor(raw_offsets).to(self.device))
+        self._prematch_truth = None
 
-    def run(self, test_titles, top_n):
+    def run(self, test_titles, top_n, with_prematch=False):
+        """-> (rows, count, features) or, with_prematch, (rows, count, features, ratios) where ratios int32[Q * top_n]
+        is Prediction._get_levenshtein_ratio of every (title, candidate) pair (predict.py:147-156, the input of the
+        "very close match" selection :172-176)."""
         import torch
         enc = encode.encode_canonical_device(test_titles, None, device=self.device.index, truth_table=self.truth_table)
         index = TruthIndex(enc['t_ptr'], enc['t_cols'], enc['idf64'], device=self.device.index)
@@ -57,4 +61,11 @@ class CandidatePipeline:
         truth_index = rows.reshape(-1).clamp(min=0).to(torch.int32)
         features = fe.construct_features_pairs((test_codes, test_offsets), (self.truth_codes, self.truth_offsets), self.word_counts,
                                                title_index, truth_index, fe.SPACE_CODE, len(self.truth_titles))
-        return rows, count, features
+        if not with_prematch:
+            return rows, count, features
+        from . import predict
+        if self._prematch_truth is None:
+            self._prematch_truth = predict.PrematchTables(self.truth_titles, device=self.device.index)
+        ratios = predict.get_levenshtein_ratios_indexed(predict.PrematchTables(test_titles, device=self.device.index),
+                                                        self._prematch_truth, title_index, truth_index)
+        return rows, count, features, ratios

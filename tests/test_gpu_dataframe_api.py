@@ -120,8 +120,8 @@ def test_candidate_pipeline_end_to_end(example_titles):
     from oracle import oracle
     truth, test = example_titles['truth_titles'], example_titles['test_titles'][:300]
     k = 10
-    rows, count, feats = CandidatePipeline(truth).run(test, k)
-    rows, feats = rows.cpu().numpy(), feats.cpu().numpy()
+    rows, count, feats, ratios = CandidatePipeline(truth).run(test, k, with_prematch=True)
+    rows, feats, ratios = rows.cpu().numpy(), feats.cpu().numpy(), ratios.cpu().numpy()
     enc = encode.encode_canonical(test, truth)
     want_rows, _, _ = oracle.topn(oracle_index_from_encoded(enc), k)
     assert np.array_equal(rows, want_rows)
@@ -133,6 +133,7 @@ def test_candidate_pipeline_end_to_end(example_titles):
     want = oracle.construct_features(la, lb, a, b, truth_word_counts(truth)[pairs_t], fe.SPACE_CODE, len(truth))
     from tests.conftest import features_equal
     assert features_equal(feats, want)
+    assert np.array_equal(ratios, np.array([oracle.prematch_ratio(test[q], truth[t]) for q, t in zip(pairs_q, pairs_t)]))
 
 
 def test_indexed_prematch_matches_per_pair_form(example_titles, golden_matchmaker):
