@@ -37,6 +37,7 @@ struct ScanProfile {
     bool enabled = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
     double pairs = 0.0;
+    int64_t post_launches = 0;   // how many of the events are k_post launches
 };
 static ScanProfile g_profile;
 
@@ -53,6 +54,14 @@ constexpr int FIXED_ROWS = 1024;    // chunk rows of the bounded-memory fallback
 constexpr int QUERY_BATCH = 65536;  // queries per workspace batch
 constexpr int STATE_OVERFLOW = 1;
 constexpr int SORT_BLOCK = 4096;    // rows are length-sorted inside blocks of this many consecutive rows
+constexpr int POST_ROWS = 2048;     // row positions per posting block = f32 accumulators per warp in k_post (8 KB)
+constexpr int POST_WARPS = 13;      // warps per CTA; two CTAs (26 warps, 213 KB of accumulators) per SM
+constexpr int POST_LIST = 64;       // per warp: rows of the swept block waiting for the full filter
+constexpr int POST_RUN = 8;         // consecutive posting blocks per warp task (the query's columns are loaded once)
+constexpr int POST_DEPTH = 4;       // posting pieces (<= 64 postings each) in flight per warp
+constexpr int POST_GROUPS = POST_ROWS / 128;   // the block sweep takes 128 rows at a time (<= 32 groups: one lane each)
+constexpr int POST_CTAS = POST_ROWS <= 2048 ? 2 : 1;
+static_assert(SORT_BLOCK % POST_ROWS == 0 && POST_GROUPS <= 32, "posting blocks must tile the sort blocks");
 constexpr int MODE_SCORE = 0;       // retained list = best m by (score, row); drives the running threshold
 constexpr int MODE_ROW = 1;         // retained list = the k highest rows with s64 >= a fixed threshold (rescan)
 
@@ -73,6 +82,16 @@ struct Index {
     float *sums = nullptr;          // [n_truth] sums_matrix_truth by original row
     float *w32 = nullptr;           // [n_vocab + 1], w32[n_vocab] = 0 (sentinel)
     double *w64 = nullptr;          // [n_vocab]
+    // The same rows inverted (k_post): for every block of POST_ROWS positions and every column id, the
+    // block-local positions of the rows holding that column.  Segment (block s, column c) is
+    // post[seg_base[s] + seg_off[s * (n_vocab + 1) + c] .. seg_base[s] + seg_off[s * (n_vocab + 1) + c + 1]).
+    // Null when the index is small, a weight or a row sum is negative / NaN (partial sums must grow and the
+    // filter's right-hand side must not fall below b), a row repeats a column or a block holds > 65,535 postings.
+    uint16_t *post = nullptr;
+    uint16_t *seg_off = nullptr;
+    uint32_t *seg_base = nullptr;
+    float *sums_floor = nullptr;    // [n_sub * POST_GROUPS] smallest sums_pos of every group of 128 positions (+inf padded)
+    int n_sub = 0;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -113,10 +132,38 @@ __device__ __forceinline__ bool better(double sa, int64_t ra, double sb, int64_t
 // ---------------------------------------------------------------------------------------------------
 // index build kernels
 // ---------------------------------------------------------------------------------------------------
-__global__ void k_weights(const double *__restrict__ w64, float *__restrict__ w32, int n_vocab) {
+__global__ void k_weights(const double *__restrict__ w64, float *__restrict__ w32, int n_vocab, int *__restrict__ not_monotone) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_vocab) w32[i] = (float)w64[i];  // numpy astype(float32): round to nearest even
+    if (i < n_vocab) {
+        const float w = (float)w64[i];  // numpy astype(float32): round to nearest even
+        w32[i] = w;
+        if (!(w >= 0.0f)) atomicOr(not_monotone, 1);   // negative / NaN idf: partial sums may decrease (k_post needs growth)
+    }
     if (i == n_vocab) w32[i] = 0.0f;
+}
+
+// Postings of the packed rows, one thread per row position.  PASS 0 counts the (block, column) segment sizes
+// into `seg`; PASS 1 appends the block-local position to each of its segments (`seg` = running cursors).
+template <int PASS>
+__global__ void k_post_build(const uint16_t *__restrict__ packed, const uint32_t *__restrict__ chunk_ptr, int64_t n_rows,
+                             int n_vocab, uint32_t *__restrict__ seg, uint16_t *__restrict__ post, int *__restrict__ repeated) {
+    int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= n_rows) return;
+    const uint16_t *cols = packed + (size_t)chunk_ptr[pos] * CHUNK_COLS;
+    const int n = (int)(chunk_ptr[pos + 1] - chunk_ptr[pos]) * CHUNK_COLS;
+    uint32_t *block_seg = seg + (size_t)(pos / POST_ROWS) * n_vocab;
+    int prev = -1;
+    for (int i = 0; i < n; ++i) {
+        const int col = cols[i];
+        if (col >= n_vocab) break;   // sentinel padding: ascending, so nothing follows
+        if (PASS == 0) {
+            if (col == prev) atomicOr(repeated, 1);
+            atomicAdd(block_seg + col, 1u);
+        } else {
+            post[atomicAdd(block_seg + col, 1u)] = (uint16_t)(pos % POST_ROWS);
+        }
+        prev = col;
+    }
 }
 
 // one thread per row: chunk count and (optionally) sums_matrix_truth = sequential f32 sum in the
@@ -124,7 +171,7 @@ __global__ void k_weights(const double *__restrict__ w64, float *__restrict__ w3
 __global__ void k_row_prepare(const int64_t *__restrict__ row_ptr, const uint16_t *__restrict__ cols,
                               const float *__restrict__ w32, int n_vocab, int64_t n_rows, const int32_t *__restrict__ perm,
                               uint32_t *__restrict__ n_chunks, float *__restrict__ sums, float *__restrict__ sums_pos,
-                              int compute_sums) {
+                              int compute_sums, int *__restrict__ not_monotone) {
     int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= n_rows) return;
     const int64_t r = perm[pos];
@@ -138,6 +185,7 @@ __global__ void k_row_prepare(const int64_t *__restrict__ row_ptr, const uint16_
         acc = sums[r];
     }
     sums_pos[pos] = acc;
+    if (!(acc >= 0.0f)) atomicOr(not_monotone, 1);
 }
 
 // one warp per row: rank-sort the row's column ids ascending into its sentinel padded chunks
@@ -164,6 +212,34 @@ __global__ void k_row_pack(const int64_t *__restrict__ row_ptr, const uint16_t *
         }
         dst[rank] = x;
     }
+}
+
+// smallest row sum of every group of 128 consecutive positions (one warp per group)
+__global__ void k_sums_floor(const float *__restrict__ sums_pos, int64_t n_rows, int64_t n_groups, float *__restrict__ out) {
+    int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+    int lane = threadIdx.x & 31;
+    if (group >= n_groups) return;
+    float low = __int_as_float(0x7f800000);
+    for (int i = lane; i < 128; i += 32) {
+        int64_t pos = group * 128 + i;
+        if (pos < n_rows) low = fminf(low, sums_pos[pos]);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) low = fminf(low, __shfl_xor_sync(0xffffffffu, low, d));
+    if (lane == 0) out[group] = low;
+}
+
+// 32-bit segment starts -> per block base + 16-bit offsets (half the table k_post has to keep in L2)
+__global__ void k_post_offsets(const uint32_t *__restrict__ seg_start, int n_sub, int n_vocab, uint16_t *__restrict__ seg_off,
+                               uint32_t *__restrict__ seg_base, int *__restrict__ too_long) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n_sub * (n_vocab + 1)) return;
+    const int s = (int)(i / (n_vocab + 1)), c = (int)(i % (n_vocab + 1));
+    const uint32_t base = seg_start[(size_t)s * n_vocab];
+    const uint32_t off = seg_start[(size_t)s * n_vocab + c] - base;   // c == n_vocab: the start of the next block
+    if (off > 65535u) atomicOr(too_long, 1);
+    seg_off[i] = (uint16_t)off;
+    if (c == 0) seg_base[s] = base;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -381,6 +457,234 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) k_scan(ScanParams p) {
         c0 = n0;
         c1 = n1;
         sum_t = next_sum;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1 posting kernel: the same scores and the same candidates as k_scan's filter pass, from the inverted
+// rows.  One warp task = one query x a run of consecutive blocks of POST_ROWS row positions.  Per block:
+// an f32 accumulator per position in shared memory; the query's columns are walked in ASCENDING id order
+// and every posting of a column adds idf32 to its row - per (query, row) pair that is the reference's
+// float32 accumulation order (match_maker.py:33-47), but only the ~2 % of the (row, column) incidences
+// that hit the query are touched instead of every column of every row.  A row appears once per segment,
+// so the lanes of a piece never collide; __syncwarp() orders consecutive pieces.  Postings are requested
+// POST_DEPTH pieces ahead of their use, the next block's segment bounds one block ahead.
+// After the last column the block is swept (and zeroed): with weights and row sums >= 0, k_scan's filter
+// `sc > fmaf(a, sums, b)` implies sc > b, so only rows above b are listed for the full test.
+// ---------------------------------------------------------------------------------------------------
+struct PostParams {
+    const uint16_t *post;
+    const uint16_t *seg_off;
+    const uint32_t *seg_base;
+    int n_vocab;
+    const float *sums;          // by position
+    const float *sums_floor;    // [blocks * POST_GROUPS] smallest row sum of every group of 128 positions
+    const float *w32;
+    const uint16_t *q_sorted;
+    const int64_t *q_ptr;
+    const int32_t *batch_q;
+    const float2 *ab;
+    int n_batch;
+    int s0, s1;                 // posting blocks of this launch
+    int run_len;                // blocks per task
+    long long n_tasks;          // runs x n_batch, the query index fastest
+    int tasks_per_cta;
+    uint2 *cand;
+    int *cand_count;
+    int cap;
+};
+
+struct PostPiece {
+    uint32_t r0, r1;   // block-local rows of this lane's postings (entries lane and lane + 32 of the piece)
+    float w;
+    int n;             // postings in the piece (warp uniform); 0 = the stream has ended
+};
+
+// full filter for the listed rows of a swept block (kept out of line: the sweep loop stays small)
+__device__ __noinline__ void post_flush(float *acc, const uint16_t *list, int n_list, int base_pos, float2 ab,
+                                        const float *__restrict__ sums, int *cand_count, uint2 *cand, int cap, int b) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    for (int i = lane; i < n_list; i += 32) {
+        const int r = list[i];
+        const float sc = acc[r];
+        acc[r] = 0.0f;
+        const int pos = base_pos + r;
+        if (sc > fmaf(ab.x, sums[pos], ab.y)) {
+            const int at = atomicAdd(cand_count + b, 1);
+            if (at < cap) cand[(size_t)b * cap + at] = make_uint2((uint32_t)pos, __float_as_uint(sc));
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(POST_WARPS * 32, POST_CTAS) k_post(PostParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_next;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *acc = reinterpret_cast<float *>(smem) + (size_t)warp * POST_ROWS;
+    float4 *acc4 = reinterpret_cast<float4 *>(acc);
+    uint16_t *list = reinterpret_cast<uint16_t *>(smem + (size_t)POST_WARPS * POST_ROWS * 4) + warp * POST_LIST;
+    if (threadIdx.x == 0) s_next = 0;
+    __syncthreads();
+    const long long cta_first = (long long)blockIdx.x * p.tasks_per_cta;
+    const int cta_tasks = (int)min((long long)p.tasks_per_cta, p.n_tasks - cta_first);
+    const unsigned lanes_below = (1u << lane) - 1u;
+    const int stride = p.n_vocab + 1;
+    const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+    for (int i = 0; i < POST_GROUPS; ++i) acc4[i * 32 + lane] = zero4;   // every sweep leaves the block zeroed again
+    __syncwarp();
+
+    for (;;) {
+        int local = 0;
+        if (lane == 0) local = atomicAdd(&s_next, 1);
+        local = __shfl_sync(0xffffffffu, local, 0);
+        if (local >= cta_tasks) break;
+        const long long task = cta_first + local;
+        const int run = (int)(task / p.n_batch);
+        const int b = (int)(task % p.n_batch);
+        const float2 ab = p.ab[b];
+        if (!(ab.y < __int_as_float(0x7f800000))) continue;   // overflowed / dense-only query: nothing can pass
+        const int s_begin = p.s0 + run * p.run_len;
+        const int s_end = min(p.s1, s_begin + p.run_len);
+        const int q = p.batch_q[b];
+        const int64_t q0 = p.q_ptr[q];
+        const int g = (int)(p.q_ptr[q + 1] - q0);
+
+        // up to 32 columns stay in registers for the whole run: lane = column
+        const bool cached = g <= 32;
+        int col = p.n_vocab;
+        float col_w = 0.0f;
+        uint32_t next_beg = 0, next_end = 0;
+        if (cached && lane < g) col = p.q_sorted[q0 + lane];
+        if (col < p.n_vocab) {
+            col_w = __ldg(p.w32 + col);
+            const uint16_t *o = p.seg_off + (size_t)s_begin * stride + col;
+            next_beg = __ldg(o);
+            next_end = __ldg(o + 1);
+        }
+        uint32_t next_base = __ldg(p.seg_base + s_begin);
+        // lane i (mod POST_GROUPS): the smallest row sum of the block's i-th group of 128 rows
+        float next_floor = __ldg(p.sums_floor + (size_t)s_begin * POST_GROUPS + (lane % POST_GROUPS));
+        int n_list = 0;
+
+        for (int s = s_begin; s < s_end; ++s) {
+            const uint32_t base = next_base;
+            // k_scan's filter with the group's smallest row sum: fmaf is monotone in sums (a >= 0), so a row that
+            // passes the filter is above its group's bar
+            const float my_bar = fmaf(ab.x, next_floor, ab.y);
+            if (s + 1 < s_end) {
+                next_base = __ldg(p.seg_base + s + 1);
+                next_floor = __ldg(p.sums_floor + (size_t)(s + 1) * POST_GROUPS + (lane % POST_GROUPS));
+            }
+            for (int g0 = 0; g0 < g; g0 += 32) {
+                uint32_t my_beg = 0, my_end = 0;
+                float my_w = 0.0f;
+                if (cached) {
+                    my_beg = next_beg;
+                    my_end = next_end;
+                    my_w = col_w;
+                    if (s + 1 < s_end && col < p.n_vocab) {
+                        const uint16_t *o = p.seg_off + (size_t)(s + 1) * stride + col;
+                        next_beg = __ldg(o);
+                        next_end = __ldg(o + 1);
+                    }
+                } else {
+                    int c = p.n_vocab;
+                    if (g0 + lane < g) c = p.q_sorted[q0 + g0 + lane];
+                    if (c < p.n_vocab) {
+                        const uint16_t *o = p.seg_off + (size_t)s * stride + c;
+                        my_beg = __ldg(o);
+                        my_end = __ldg(o + 1);
+                        my_w = __ldg(p.w32 + c);
+                    }
+                }
+                unsigned pending = __ballot_sync(0xffffffffu, my_end > my_beg);   // non-empty segments, ascending column id
+                uint32_t cur = 0, end = 0;   // warp-uniform cursor into the current segment
+                float w = 0.0f;
+
+                auto fill = [&](PostPiece &piece) {
+                    if (cur >= end) {
+                        if (pending == 0) {
+                            piece.n = 0;
+                            return;
+                        }
+                        const int j = __ffs(pending) - 1;
+                        pending &= pending - 1;
+                        cur = base + __shfl_sync(0xffffffffu, my_beg, j);
+                        end = base + __shfl_sync(0xffffffffu, my_end, j);
+                        w = __shfl_sync(0xffffffffu, my_w, j);
+                    }
+                    const int n = (int)min(end - cur, 64u);
+                    piece.n = n;
+                    piece.w = w;
+                    piece.r0 = 0;
+                    piece.r1 = 0;
+                    if (lane < n) piece.r0 = __ldg(p.post + cur + lane);
+                    if (lane + 32 < n) piece.r1 = __ldg(p.post + cur + lane + 32);
+                    cur += 64;
+                };
+                auto consume = [&](const PostPiece &piece) {
+                    const bool first = lane < piece.n, second = lane + 32 < piece.n;
+                    float a0 = 0.0f, a1 = 0.0f;
+                    if (first) a0 = acc[piece.r0];
+                    if (second) a1 = acc[piece.r1];
+                    if (first) acc[piece.r0] = __fadd_rn(a0, piece.w);
+                    if (second) acc[piece.r1] = __fadd_rn(a1, piece.w);
+                    __syncwarp();   // the next piece may belong to the next column and touch the same rows
+                };
+
+                PostPiece ring[POST_DEPTH];
+#pragma unroll
+                for (int d = 0; d < POST_DEPTH; ++d) fill(ring[d]);
+                bool running = true;
+                while (running) {
+#pragma unroll
+                    for (int d = 0; d < POST_DEPTH; ++d) {
+                        if (ring[d].n == 0) {
+                            running = false;
+                            break;
+                        }
+                        consume(ring[d]);
+                        fill(ring[d]);
+                    }
+                }
+            }
+
+            // sweep and zero the block, 128 rows (4 per lane) at a time; rows above their group's bar wait in `list`
+            // (their accumulators stay) for the full filter
+            const int base_pos = s * POST_ROWS;
+#pragma unroll 1
+            for (int i = 0; i < POST_GROUPS; ++i) {
+                const int idx = i * 32 + lane;
+                const float bar = __shfl_sync(0xffffffffu, my_bar, i);
+                const float4 v = acc4[idx];
+                const bool hit = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) > bar;
+                if (__ballot_sync(0xffffffffu, hit) == 0) {
+                    acc4[idx] = zero4;
+                    continue;
+                }
+                const float vals[4] = {v.x, v.y, v.z, v.w};
+                acc4[idx] = make_float4(v.x > bar ? v.x : 0.0f, v.y > bar ? v.y : 0.0f, v.z > bar ? v.z : 0.0f, v.w > bar ? v.w : 0.0f);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const bool above = vals[c] > bar;
+                    const unsigned above_mask = __ballot_sync(0xffffffffu, above);
+                    if (n_list + __popc(above_mask) > POST_LIST) {
+                        post_flush(acc, list, n_list, base_pos, ab, p.sums, p.cand_count, p.cand, p.cap, b);
+                        n_list = 0;
+                    }
+                    if (above) list[n_list + __popc(above_mask & lanes_below)] = (uint16_t)(idx * 4 + c);
+                    n_list += __popc(above_mask);
+                }
+            }
+            if (n_list > 0) {
+                post_flush(acc, list, n_list, base_pos, ab, p.sums, p.cand_count, p.cand, p.cap, b);
+                n_list = 0;
+            }
+            __syncwarp();
+        }
     }
 }
 
@@ -843,6 +1147,46 @@ static int launch_scan(const Index &ix, cudaStream_t stream, ScanParams sp, int 
     return DS_OK;
 }
 
+// posting blocks [s0, s1) for every batch query; counted with k_scan in the profile (same pairs, same role)
+static int launch_post(const Index &ix, cudaStream_t stream, PostParams pp, int s0, int s1) {
+    if (s1 <= s0 || pp.n_batch <= 0) return DS_OK;
+    pp.post = ix.post;
+    pp.seg_off = ix.seg_off;
+    pp.seg_base = ix.seg_base;
+    pp.n_vocab = ix.n_vocab;
+    pp.sums = ix.sums_pos;
+    pp.sums_floor = ix.sums_floor;
+    pp.w32 = ix.w32;
+    pp.s0 = s0;
+    pp.s1 = s1;
+    // a task = one query x a run of blocks: long runs amortise the query set-up, short ones keep small batches parallel
+    const long long wanted_tasks = (long long)148 * 2 * POST_WARPS * 2;
+    pp.run_len = (int)std::min<long long>(POST_RUN, std::max<long long>(1, (long long)(s1 - s0) * pp.n_batch / wanted_tasks));
+    pp.n_tasks = ceil_div(s1 - s0, pp.run_len) * (long long)pp.n_batch;
+    // tasks are handed out warp by warp inside a CTA; several per warp level the very uneven task lengths
+    pp.tasks_per_cta = (int)std::min<long long>(POST_WARPS * 4, std::max<long long>(POST_WARPS, ceil_div(pp.n_tasks, (long long)148 * 2 * 2)));
+    const long long ctas = ceil_div(pp.n_tasks, (long long)pp.tasks_per_cta);
+    if (ctas > INT32_MAX) return fail(DS_ERR_UNSUPPORTED, "too many posting tasks in one launch");
+    const size_t smem = (size_t)POST_WARPS * (POST_ROWS * 4 + POST_LIST * 2);
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    if (g_profile.enabled) {
+        DS_CUDA(cudaEventCreate(&ev_start));
+        DS_CUDA(cudaEventCreate(&ev_stop));
+        DS_CUDA(cudaEventRecord(ev_start, stream));
+    }
+    DS_CHECK(ensure_dynamic_smem(reinterpret_cast<const void *>(&k_post), smem));
+    k_post<<<(unsigned)ctas, POST_WARPS * 32, smem, stream>>>(pp);
+    DS_LAUNCHED("k_post");
+    if (g_profile.enabled) {
+        DS_CUDA(cudaEventRecord(ev_stop, stream));
+        g_profile.events.emplace_back(ev_start, ev_stop);
+        const int64_t rows = std::min<int64_t>(ix.n_truth, (int64_t)s1 * POST_ROWS) - (int64_t)s0 * POST_ROWS;
+        g_profile.pairs += (double)rows * (double)pp.n_batch;
+        g_profile.post_launches += 1;
+    }
+    return DS_OK;
+}
+
 static int launch_select(cudaStream_t stream, SelectParams sp) {
     if (sp.n_batch <= 0) return DS_OK;
     int items = std::max(sp.cap, sp.dense_rows) + sp.m;
@@ -929,6 +1273,16 @@ static int run_pipeline(Workspace &call_ws, const Index &ix, const QuerySet &qs,
     sp.cap = cand_cap;
     sp.dense_stride = dense_rows;
 
+    PostParams pp{};
+    pp.q_sorted = qs.d_sorted;
+    pp.q_ptr = qs.d_ptr;
+    pp.batch_q = d_batch;
+    pp.ab = d_ab;
+    pp.n_batch = n_batch;
+    pp.cand = d_cand;
+    pp.cand_count = d_cand_count;
+    pp.cap = cand_cap;
+
     SelectParams sel{};
     sel.mode = mode;
     sel.batch_q = d_batch;
@@ -959,11 +1313,22 @@ static int run_pipeline(Workspace &call_ws, const Index &ix, const QuerySet &qs,
         int64_t r1;
         if (dense) r1 = std::min<int64_t>(n, r0 + dense_rows);
         else if (mode == MODE_ROW) r1 = n;  // the threshold is fixed: one pass over all rows
-        else r1 = std::min<int64_t>(n, std::max<int64_t>(2 * r0, r0 + dense_rows));   // doubling sweep: thresholds tighten early (x4 overflows the candidate buffers)
-        sp.r0 = (int)r0;
-        sp.r1 = (int)r1;
-        sp.dense = dense ? d_dense : nullptr;
-        DS_CHECK(launch_scan(ix, stream, sp, n_tiles, n_batch));
+        else {
+            // doubling sweep: thresholds tighten early (x4 overflows the candidate buffers); past the first posting
+            // block the ranges end on block boundaries so that k_post can take them
+            r1 = std::max<int64_t>(2 * r0, r0 + dense_rows);
+            if (r1 > POST_ROWS) r1 = ceil_div(r1, (int64_t)POST_ROWS) * POST_ROWS;
+            r1 = std::min<int64_t>(n, r1);
+        }
+        const bool inverted = !dense && ix.post != nullptr && r0 % POST_ROWS == 0 && (r0 >= 2 * POST_ROWS || mode == MODE_ROW);
+        if (inverted) {
+            DS_CHECK(launch_post(ix, stream, pp, (int)(r0 / POST_ROWS), (int)ceil_div(r1, (int64_t)POST_ROWS)));
+        } else {
+            sp.r0 = (int)r0;
+            sp.r1 = (int)r1;
+            sp.dense = dense ? d_dense : nullptr;
+            DS_CHECK(launch_scan(ix, stream, sp, n_tiles, n_batch));
+        }
         sel.dense = dense ? d_dense : nullptr;
         sel.dense_rows = dense ? (int)(r1 - r0) : 0;
         sel.dense_r0 = (int)r0;
@@ -1086,6 +1451,7 @@ int ds_profile_begin(void) {
     }
     g_profile.events.clear();
     g_profile.pairs = 0.0;
+    g_profile.post_launches = 0;
     g_profile.enabled = true;
     return DS_OK;
 }
@@ -1191,7 +1557,10 @@ int ds_index_create(ds_index **out, int device, int64_t n_truth, int32_t n_vocab
         DS_CUDA(cudaMemcpyAsync(ix.perm, h_perm.data(), (size_t)n_truth * 4, cudaMemcpyHostToDevice, stream));
         DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.chunk_ptr), ((size_t)n_truth + 1) * 4, stream));
         DS_CUDA(cudaMemcpyAsync(ix.w64, d_w64_in, (size_t)n_vocab * 8, cudaMemcpyDeviceToDevice, stream));
-        k_weights<<<(unsigned)ceil_div(n_vocab + 1, 256), 256, 0, stream>>>(ix.w64, ix.w32, n_vocab);
+        int *d_post_flags = nullptr;   // [0]: a weight or row sum is negative / NaN, [1]: a row repeats a column, [2]: a block is too long
+        DS_CHECK(ws.alloc(&d_post_flags, 3));
+        DS_CUDA(cudaMemsetAsync(d_post_flags, 0, 12, stream));
+        k_weights<<<(unsigned)ceil_div(n_vocab + 1, 256), 256, 0, stream>>>(ix.w64, ix.w32, n_vocab, d_post_flags);
         DS_LAUNCHED("k_weights");
         uint32_t *d_counts = nullptr;
         DS_CHECK(ws.alloc(&d_counts, (size_t)n_truth + 1));
@@ -1200,7 +1569,7 @@ int ds_index_create(ds_index **out, int device, int64_t n_truth, int32_t n_vocab
             if (d_sums_in != nullptr)
                 DS_CUDA(cudaMemcpyAsync(ix.sums, d_sums_in, (size_t)n_truth * 4, cudaMemcpyDeviceToDevice, stream));
             k_row_prepare<<<(unsigned)ceil_div(n_truth, 256), 256, 0, stream>>>(d_ptr, d_cols, ix.w32, n_vocab, n_truth, ix.perm, d_counts,
-                                                                               ix.sums, ix.sums_pos, d_sums_in == nullptr ? 1 : 0);
+                                                                               ix.sums, ix.sums_pos, d_sums_in == nullptr ? 1 : 0, d_post_flags);
             DS_LAUNCHED("k_row_prepare");
         }
         size_t temp_bytes = 0;
@@ -1220,7 +1589,50 @@ int ds_index_create(ds_index **out, int device, int64_t n_truth, int32_t n_vocab
                                                                                  (uint16_t)n_vocab, reinterpret_cast<uint16_t *>(ix.chunks));
             DS_LAUNCHED("k_row_pack");
         }
+        // inverted form for k_post (skipped for small indexes: the dense sweep of the first rows covers them)
+        const int64_t n_sub = ceil_div(n_truth, (int64_t)POST_ROWS);
+        const int64_t n_seg = n_sub * n_vocab;
+        if (n_truth > 2 * POST_ROWS && n_seg < ((int64_t)1 << 30) && (uint64_t)total_chunks * CHUNK_COLS < ((uint64_t)1 << 32) - 256) {
+            ix.n_sub = (int)n_sub;
+            uint32_t *d_seg_start = nullptr;
+            unsigned char *d_seg_temp = nullptr;
+            DS_CHECK(ws.alloc(&d_seg_start, (size_t)n_seg + 1));
+            DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.seg_off), (size_t)n_sub * (n_vocab + 1) * 2, stream));
+            DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.seg_base), (size_t)n_sub * 4, stream));
+            DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.sums_floor), (size_t)n_sub * POST_GROUPS * 4, stream));
+            k_sums_floor<<<(unsigned)ceil_div(n_sub * POST_GROUPS * 32, 256), 256, 0, stream>>>(ix.sums_pos, n_truth, n_sub * POST_GROUPS, ix.sums_floor);
+            DS_LAUNCHED("k_sums_floor");
+            DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.post), std::max<size_t>(1, (size_t)total_chunks * CHUNK_COLS) * 2, stream));
+            DS_CUDA(cudaMemsetAsync(d_seg_start, 0, ((size_t)n_seg + 1) * 4, stream));
+            const uint16_t *packed = reinterpret_cast<const uint16_t *>(ix.chunks);
+            k_post_build<0><<<(unsigned)ceil_div(n_truth, 256), 256, 0, stream>>>(packed, ix.chunk_ptr, n_truth, n_vocab, d_seg_start, nullptr,
+                                                                                  d_post_flags + 1);
+            DS_LAUNCHED("k_post_build");
+            size_t seg_temp_bytes = 0;
+            DS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, seg_temp_bytes, d_seg_start, d_seg_start, (int)(n_seg + 1), stream));
+            DS_CHECK(ws.alloc(&d_seg_temp, seg_temp_bytes));
+            DS_CUDA(cub::DeviceScan::ExclusiveSum(d_seg_temp, seg_temp_bytes, d_seg_start, d_seg_start, (int)(n_seg + 1), stream));
+            g_kernel_launches.fetch_add(1);
+            k_post_offsets<<<(unsigned)ceil_div(n_sub * (n_vocab + 1), 256), 256, 0, stream>>>(d_seg_start, (int)n_sub, n_vocab, ix.seg_off,
+                                                                                              ix.seg_base, d_post_flags + 2);
+            DS_LAUNCHED("k_post_offsets");
+            k_post_build<1><<<(unsigned)ceil_div(n_truth, 256), 256, 0, stream>>>(packed, ix.chunk_ptr, n_truth, n_vocab, d_seg_start, ix.post,
+                                                                                  d_post_flags + 1);   // d_seg_start = running cursors from here on
+            DS_LAUNCHED("k_post_build");
+        }
+        int h_post_flags[3] = {0, 0, 0};
+        DS_CUDA(cudaMemcpyAsync(h_post_flags, d_post_flags, 12, cudaMemcpyDeviceToHost, stream));
         DS_CUDA(cudaStreamSynchronize(stream));
+        if ((h_post_flags[0] != 0 || h_post_flags[1] != 0 || h_post_flags[2] != 0) && ix.post != nullptr) {
+            cudaFreeAsync(ix.post, stream);
+            cudaFreeAsync(ix.seg_off, stream);
+            cudaFreeAsync(ix.seg_base, stream);
+            cudaFreeAsync(ix.sums_floor, stream);
+            ix.sums_floor = nullptr;
+            ix.post = nullptr;
+            ix.seg_off = nullptr;
+            ix.seg_base = nullptr;
+        }
         return DS_OK;
     }();
     if (status != DS_OK) {
@@ -1236,7 +1648,8 @@ int ds_index_destroy(ds_index *index) {
     DeviceGuard guard(index->ix.device);
     // stream-ordered frees (the buffers come from the same pool as the per-call workspace): no device-wide
     // synchronisation, unlike cudaFree
-    void *buffers[] = {index->ix.chunks, index->ix.chunk_ptr, index->ix.sums, index->ix.sums_pos, index->ix.perm, index->ix.w32, index->ix.w64};
+    void *buffers[] = {index->ix.chunks, index->ix.chunk_ptr, index->ix.sums, index->ix.sums_pos, index->ix.perm, index->ix.w32, index->ix.w64,
+                       index->ix.post, index->ix.seg_off, index->ix.seg_base, index->ix.sums_floor};
     for (void *b : buffers)
         if (b != nullptr) cudaFreeAsync(b, nullptr);
     delete index;
