@@ -604,6 +604,8 @@ __global__ void __launch_bounds__(POST_WARPS * 32, POST_CTAS) k_post(PostParams 
                 uint32_t cur = 0, end = 0;   // warp-uniform cursor into the current segment
                 float w = 0.0f;
 
+                // one ring step: read the accumulators of the oldest piece, request the piece POST_DEPTH ahead (its
+                // address arithmetic covers the shared-memory latency), then add and store
                 auto fill = [&](PostPiece &piece) {
                     if (cur >= end) {
                         if (pending == 0) {
@@ -619,35 +621,43 @@ __global__ void __launch_bounds__(POST_WARPS * 32, POST_CTAS) k_post(PostParams 
                     const int n = (int)min(end - cur, 64u);
                     piece.n = n;
                     piece.w = w;
-                    piece.r0 = 0;
-                    piece.r1 = 0;
-                    if (lane < n) piece.r0 = __ldg(p.post + cur + lane);
-                    if (lane + 32 < n) piece.r1 = __ldg(p.post + cur + lane + 32);
+                    const uint16_t *src = p.post + cur + lane;
+                    if (lane < n) piece.r0 = __ldg(src);
+                    if (n > 32) {
+                        if (lane + 32 < n) piece.r1 = __ldg(src + 32);
+                    }
                     cur += 64;
                 };
-                auto consume = [&](const PostPiece &piece) {
-                    const bool first = lane < piece.n, second = lane + 32 < piece.n;
-                    float a0 = 0.0f, a1 = 0.0f;
-                    if (first) a0 = acc[piece.r0];
-                    if (second) a1 = acc[piece.r1];
-                    if (first) acc[piece.r0] = __fadd_rn(a0, piece.w);
-                    if (second) acc[piece.r1] = __fadd_rn(a1, piece.w);
-                    __syncwarp();   // the next piece may belong to the next column and touch the same rows
-                };
-
                 PostPiece ring[POST_DEPTH];
 #pragma unroll
-                for (int d = 0; d < POST_DEPTH; ++d) fill(ring[d]);
+                for (int d = 0; d < POST_DEPTH; ++d) {
+                    ring[d].r0 = 0;
+                    ring[d].r1 = 0;
+                    fill(ring[d]);
+                }
                 bool running = true;
                 while (running) {
 #pragma unroll
                     for (int d = 0; d < POST_DEPTH; ++d) {
-                        if (ring[d].n == 0) {
+                        const int n = ring[d].n;
+                        if (n == 0) {
                             running = false;
                             break;
                         }
-                        consume(ring[d]);
+                        const float add = ring[d].w;
+                        float *slot0 = acc + ring[d].r0, *slot1 = acc + ring[d].r1;
+                        const bool first = lane < n, second = lane + 32 < n;
+                        float a0 = 0.0f, a1 = 0.0f;
+                        if (first) a0 = *slot0;
+                        if (n > 32) {
+                            if (second) a1 = *slot1;
+                        }
                         fill(ring[d]);
+                        if (first) *slot0 = __fadd_rn(a0, add);
+                        if (n > 32) {
+                            if (second) *slot1 = __fadd_rn(a1, add);
+                        }
+                        __syncwarp();   // the next piece may belong to the next column and touch the same rows
                     }
                 }
             }
