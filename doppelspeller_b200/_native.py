@@ -23,7 +23,7 @@ MAX_TITLE = 255
 
 # every symbol include/doppelspeller_b200.h declares (tests check that the library exports them all)
 EXPORTED_SYMBOLS = (
-    'ds_version', 'ds_last_error', 'ds_kernel_launches', 'ds_profile_begin', 'ds_profile_end',
+    'ds_version', 'ds_last_error', 'ds_kernel_launches', 'ds_profile_begin', 'ds_profile_end', 'ds_profile_end_split',
     'ds_index_create', 'ds_index_destroy', 'ds_index_get_sums',
     'ds_topn', 'ds_topn_retained', 'ds_topn_local', 'ds_topn_merge', 'ds_topn_rescan',
     'ds_indel_ratio_u8', 'ds_indel_ratio_pairs', 'ds_levenshtein_ratio_pairs',
@@ -90,6 +90,13 @@ def profile_end():
     ms, launches, pairs = ctypes.c_double(0), ctypes.c_int64(0), ctypes.c_double(0)
     check(lib.ds_profile_end(ctypes.byref(ms), ctypes.byref(launches), ctypes.byref(pairs)))
     return ms.value, launches.value, pairs.value
+
+
+def profile_end_split():
+    """-> {'k_scan': (device ms, launches, pairs), 'k_post': (...)}: the two forms of the K1 scan, timed separately"""
+    ms, launches, pairs = (ctypes.c_double * 2)(), (ctypes.c_int64 * 2)(), (ctypes.c_double * 2)()
+    check(lib.ds_profile_end_split(ms, launches, pairs))
+    return {name: (ms[i], launches[i], pairs[i]) for i, name in enumerate(('k_scan', 'k_post'))}
 
 
 def topn_retained(k):

@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cmath>
 #include <new>
+#include <type_traits>
 
 #include "ds_common.cuh"
 
@@ -35,9 +36,8 @@ std::atomic<int64_t> g_kernel_launches{0};
 // optional timing of the dominant kernel (k_scan) for bench.py's roofline: CUDA events on the launching stream
 struct ScanProfile {
     bool enabled = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
-    double pairs = 0.0;
-    int64_t post_launches = 0;   // how many of the events are k_post launches
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events[2];   // [0] k_scan launches, [1] k_post launches
+    double pairs[2] = {0.0, 0.0};
 };
 static ScanProfile g_profile;
 
@@ -61,6 +61,7 @@ constexpr int POST_RUN = 8;         // consecutive posting blocks per warp task 
 constexpr int POST_DEPTH = 4;       // posting pieces (<= 64 postings each) in flight per warp
 constexpr int POST_GROUPS = POST_ROWS / 128;   // the block sweep takes 128 rows at a time (<= 32 groups: one lane each)
 constexpr int POST_CTAS = POST_ROWS <= 2048 ? 2 : 1;
+typedef std::conditional<POST_ROWS <= 2048, uint16_t, uint32_t>::type post_off_t;   // segment offsets inside a block
 static_assert(SORT_BLOCK % POST_ROWS == 0 && POST_GROUPS <= 32, "posting blocks must tile the sort blocks");
 constexpr int MODE_SCORE = 0;       // retained list = best m by (score, row); drives the running threshold
 constexpr int MODE_ROW = 1;         // retained list = the k highest rows with s64 >= a fixed threshold (rescan)
@@ -88,7 +89,7 @@ struct Index {
     // Null when the index is small, a weight or a row sum is negative / NaN (partial sums must grow and the
     // filter's right-hand side must not fall below b), a row repeats a column or a block holds > 65,535 postings.
     uint16_t *post = nullptr;
-    uint16_t *seg_off = nullptr;
+    post_off_t *seg_off = nullptr;
     uint32_t *seg_base = nullptr;
     float *sums_floor = nullptr;    // [n_sub * POST_GROUPS] smallest sums_pos of every group of 128 positions (+inf padded)
     int n_sub = 0;
@@ -230,15 +231,15 @@ __global__ void k_sums_floor(const float *__restrict__ sums_pos, int64_t n_rows,
 }
 
 // 32-bit segment starts -> per block base + 16-bit offsets (half the table k_post has to keep in L2)
-__global__ void k_post_offsets(const uint32_t *__restrict__ seg_start, int n_sub, int n_vocab, uint16_t *__restrict__ seg_off,
+__global__ void k_post_offsets(const uint32_t *__restrict__ seg_start, int n_sub, int n_vocab, post_off_t *__restrict__ seg_off,
                                uint32_t *__restrict__ seg_base, int *__restrict__ too_long) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)n_sub * (n_vocab + 1)) return;
     const int s = (int)(i / (n_vocab + 1)), c = (int)(i % (n_vocab + 1));
     const uint32_t base = seg_start[(size_t)s * n_vocab];
     const uint32_t off = seg_start[(size_t)s * n_vocab + c] - base;   // c == n_vocab: the start of the next block
-    if (off > 65535u) atomicOr(too_long, 1);
-    seg_off[i] = (uint16_t)off;
+    if (sizeof(post_off_t) == 2 && off > 65535u) atomicOr(too_long, 1);
+    seg_off[i] = (post_off_t)off;
     if (c == 0) seg_base[s] = base;
 }
 
@@ -474,7 +475,7 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) k_scan(ScanParams p) {
 // ---------------------------------------------------------------------------------------------------
 struct PostParams {
     const uint16_t *post;
-    const uint16_t *seg_off;
+    const post_off_t *seg_off;
     const uint32_t *seg_base;
     int n_vocab;
     const float *sums;          // by position
@@ -560,7 +561,7 @@ __global__ void __launch_bounds__(POST_WARPS * 32, POST_CTAS) k_post(PostParams 
         if (cached && lane < g) col = p.q_sorted[q0 + lane];
         if (col < p.n_vocab) {
             col_w = __ldg(p.w32 + col);
-            const uint16_t *o = p.seg_off + (size_t)s_begin * stride + col;
+            const post_off_t *o = p.seg_off + (size_t)s_begin * stride + col;
             next_beg = __ldg(o);
             next_end = __ldg(o + 1);
         }
@@ -586,7 +587,7 @@ __global__ void __launch_bounds__(POST_WARPS * 32, POST_CTAS) k_post(PostParams 
                     my_end = next_end;
                     my_w = col_w;
                     if (s + 1 < s_end && col < p.n_vocab) {
-                        const uint16_t *o = p.seg_off + (size_t)(s + 1) * stride + col;
+                        const post_off_t *o = p.seg_off + (size_t)(s + 1) * stride + col;
                         next_beg = __ldg(o);
                         next_end = __ldg(o + 1);
                     }
@@ -594,7 +595,7 @@ __global__ void __launch_bounds__(POST_WARPS * 32, POST_CTAS) k_post(PostParams 
                     int c = p.n_vocab;
                     if (g0 + lane < g) c = p.q_sorted[q0 + g0 + lane];
                     if (c < p.n_vocab) {
-                        const uint16_t *o = p.seg_off + (size_t)s * stride + c;
+                        const post_off_t *o = p.seg_off + (size_t)s * stride + c;
                         my_beg = __ldg(o);
                         my_end = __ldg(o + 1);
                         my_w = __ldg(p.w32 + c);
@@ -1150,8 +1151,8 @@ static int launch_scan(const Index &ix, cudaStream_t stream, ScanParams sp, int 
         DS_LAUNCHED("k_scan");
         if (g_profile.enabled) {
             DS_CUDA(cudaEventRecord(ev_stop, stream));
-            g_profile.events.emplace_back(ev_start, ev_stop);
-            g_profile.pairs += (double)rows * (double)n_queries * ((double)nt / (double)n_tiles);
+            g_profile.events[0].emplace_back(ev_start, ev_stop);
+            g_profile.pairs[0] += (double)rows * (double)n_queries * ((double)nt / (double)n_tiles);
         }
     }
     return DS_OK;
@@ -1189,10 +1190,9 @@ static int launch_post(const Index &ix, cudaStream_t stream, PostParams pp, int 
     DS_LAUNCHED("k_post");
     if (g_profile.enabled) {
         DS_CUDA(cudaEventRecord(ev_stop, stream));
-        g_profile.events.emplace_back(ev_start, ev_stop);
+        g_profile.events[1].emplace_back(ev_start, ev_stop);
         const int64_t rows = std::min<int64_t>(ix.n_truth, (int64_t)s1 * POST_ROWS) - (int64_t)s0 * POST_ROWS;
-        g_profile.pairs += (double)rows * (double)pp.n_batch;
-        g_profile.post_launches += 1;
+        g_profile.pairs[1] += (double)rows * (double)pp.n_batch;
     }
     return DS_OK;
 }
@@ -1455,32 +1455,46 @@ extern "C" {
 int ds_version(void) { return DS_VERSION; }
 
 int ds_profile_begin(void) {
-    for (auto &e : g_profile.events) {
-        cudaEventDestroy(e.first);
-        cudaEventDestroy(e.second);
+    for (auto &events : g_profile.events) {
+        for (auto &e : events) {
+            cudaEventDestroy(e.first);
+            cudaEventDestroy(e.second);
+        }
+        events.clear();
     }
-    g_profile.events.clear();
-    g_profile.pairs = 0.0;
-    g_profile.post_launches = 0;
+    g_profile.pairs[0] = g_profile.pairs[1] = 0.0;
     g_profile.enabled = true;
     return DS_OK;
 }
 
-int ds_profile_end(double *scan_ms, int64_t *scan_launches, double *scan_pairs) {
+int ds_profile_end_split(double *ms, int64_t *launches, double *pairs) {
     g_profile.enabled = false;
-    double total = 0.0;
-    for (auto &e : g_profile.events) {
-        float ms = 0.0f;
-        DS_CUDA(cudaEventSynchronize(e.second));
-        DS_CUDA(cudaEventElapsedTime(&ms, e.first, e.second));
-        total += ms;
-        cudaEventDestroy(e.first);
-        cudaEventDestroy(e.second);
+    for (int kernel = 0; kernel < 2; ++kernel) {
+        double total = 0.0;
+        for (auto &e : g_profile.events[kernel]) {
+            float one = 0.0f;
+            DS_CUDA(cudaEventSynchronize(e.second));
+            DS_CUDA(cudaEventElapsedTime(&one, e.first, e.second));
+            total += one;
+            cudaEventDestroy(e.first);
+            cudaEventDestroy(e.second);
+        }
+        if (ms) ms[kernel] = total;
+        if (launches) launches[kernel] = (int64_t)g_profile.events[kernel].size();
+        if (pairs) pairs[kernel] = g_profile.pairs[kernel];
+        g_profile.events[kernel].clear();
     }
-    if (scan_ms) *scan_ms = total;
-    if (scan_launches) *scan_launches = (int64_t)g_profile.events.size();
-    if (scan_pairs) *scan_pairs = g_profile.pairs;
-    g_profile.events.clear();
+    return DS_OK;
+}
+
+int ds_profile_end(double *scan_ms, int64_t *scan_launches, double *scan_pairs) {
+    double ms[2];
+    int64_t launches[2];
+    double pairs[2];
+    DS_CHECK(ds_profile_end_split(ms, launches, pairs));
+    if (scan_ms) *scan_ms = ms[0] + ms[1];
+    if (scan_launches) *scan_launches = launches[0] + launches[1];
+    if (scan_pairs) *scan_pairs = pairs[0] + pairs[1];
     return DS_OK;
 }
 const char *ds_last_error(void) { return g_last_error; }
@@ -1607,7 +1621,7 @@ int ds_index_create(ds_index **out, int device, int64_t n_truth, int32_t n_vocab
             uint32_t *d_seg_start = nullptr;
             unsigned char *d_seg_temp = nullptr;
             DS_CHECK(ws.alloc(&d_seg_start, (size_t)n_seg + 1));
-            DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.seg_off), (size_t)n_sub * (n_vocab + 1) * 2, stream));
+            DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.seg_off), (size_t)n_sub * (n_vocab + 1) * sizeof(post_off_t), stream));
             DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.seg_base), (size_t)n_sub * 4, stream));
             DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.sums_floor), (size_t)n_sub * POST_GROUPS * 4, stream));
             k_sums_floor<<<(unsigned)ceil_div(n_sub * POST_GROUPS * 32, 256), 256, 0, stream>>>(ix.sums_pos, n_truth, n_sub * POST_GROUPS, ix.sums_floor);

@@ -57,10 +57,13 @@ const char *ds_last_error(void);
 /* number of CUDA kernels this library has launched in the calling process (bench.py gpu_launches) */
 int64_t ds_kernel_launches(void);
 /* Measurement hooks (bench.py roofline): between ds_profile_begin and ds_profile_end every launch of the
- * dominant kernel (the K1 scan) is bracketed by CUDA events on its own stream.  ds_profile_end waits
+ * K1 scan kernels (k_scan, k_post) is bracketed by CUDA events on its own stream.  ds_profile_end waits
  * for them and returns the summed device time, the launch count and the (query, truth) pairs scanned. */
 int ds_profile_begin(void);
 int ds_profile_end(double *scan_ms, int64_t *scan_launches, double *scan_pairs);
+/* the same, per kernel: index 0 = k_scan (dense row scan: the first rows and the fallbacks), 1 = k_post
+ * (posting-list form of the same scan, the bulk of the rows); each argument points to two elements */
+int ds_profile_end_split(double *ms, int64_t *launches, double *pairs);
 
 /* ---------------------------------------------------------------------------------------------------
  * ds_index_create  -  replaces the truth-side half of MatchMaker.__init__ (match_maker.py:97-109:

@@ -1,10 +1,11 @@
 """Turns the raw ncu outputs brought back in gpurun_out/ into the committed summaries under profiles/.
 
-    python profiles/summarize.py <round-tag> [launches.csv] [report.ncu-rep]
+    python profiles/summarize.py <round-tag> [launches.csv] [report.ncu-rep] [kernel]
 
 Writes profiles/<tag>_launches.md (every kernel of one bench step with its device time and share),
-profiles/<tag>_k_scan_metrics.csv (the ncu --set full metrics that matter, per captured launch) and
-profiles/k_scan_traffic.json (DRAM bytes per launch, read by bench.py for roofline.traffic).
+profiles/<tag>_<kernel>_metrics.csv (the ncu --set full metrics that matter, per captured launch) and
+profiles/<kernel>_traffic.json (DRAM bytes per launch, read by bench.py for roofline.traffic).  `kernel` is the
+kernel the report captured: k_post (default, the dominant one) or k_scan.
 """
 import collections
 import csv
@@ -71,12 +72,12 @@ def launches(tag, path):
     open(os.path.join(HERE, f'{tag}_launches.md'), 'w').write('\n'.join(out) + '\n')
 
 
-def metrics(tag, report):
+def metrics(tag, report, kernel):
     raw = subprocess.run(['ncu', '-i', report, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     header, units = rows[0], rows[1]
     picked = [m for m in METRICS if m in header]
-    with open(os.path.join(HERE, f'{tag}_k_scan_metrics.csv'), 'w', newline='') as f:
+    with open(os.path.join(HERE, f'{tag}_{kernel}_metrics.csv'), 'w', newline='') as f:
         w = csv.writer(f)
         w.writerow(['metric', 'unit'] + [f'launch_{i}' for i in range(len(rows) - 2)])
         for m in picked:
@@ -89,12 +90,13 @@ def metrics(tag, report):
             i = header.index(m)
             total += to_bytes(r[i], units[i])
         dram.append(total)
-    json.dump({'kernel': 'k_scan', 'dram_bytes_per_launch': sum(dram) / len(dram), 'captured_launches': dram,
-               'source': f'profiles/{tag}_k_scan_metrics.csv (ncu --set full --clock-control none)'},
-              open(os.path.join(HERE, 'k_scan_traffic.json'), 'w'), indent=1)
+    json.dump({'kernel': kernel, 'dram_bytes_per_launch': sum(dram) / len(dram), 'captured_launches': dram,
+               'source': f'profiles/{tag}_{kernel}_metrics.csv (ncu --set full --clock-control none)'},
+              open(os.path.join(HERE, f'{kernel}_traffic.json'), 'w'), indent=1)
 
 
 if __name__ == '__main__':
     tag = sys.argv[1]
     launches(tag, sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, 'gpurun_out', 'launches_r1.csv'))
-    metrics(tag, sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, 'gpurun_out', 'prof_scan_r1.ncu-rep'))
+    metrics(tag, sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, 'gpurun_out', 'prof_scan_r1.ncu-rep'),
+            sys.argv[4] if len(sys.argv) > 4 else 'k_post')

@@ -53,6 +53,24 @@ def test_candidates_match_oracle_synthetic(n_truth, n_q, k, seed):
     assert np.array_equal(kth, want_kth)
 
 
+def test_negative_weight_keeps_the_dense_scan():
+    """The posting-list kernel needs partial sums that only grow; an index with a negative idf weight must stay on
+    the dense row scan and still reproduce the oracle (scores of rows holding that column shrink)."""
+    from doppelspeller_b200 import encode, synthetic
+    from oracle import oracle
+    truth = synthetic.generate_truth_titles(12000, seed=61)
+    test, _ = synthetic.generate_test_titles(truth, 300, seed=62)
+    enc = encode.encode_canonical(test, truth)
+    enc['idf64'] = enc['idf64'].copy()
+    common = int(np.bincount(enc['t_cols'].astype(np.int64)).argmax())
+    enc['idf64'][common] = -0.75
+    rows, count, kth, _ = _match_maker(enc, 10)._index.topn(enc['q_ptr'], enc['q_cols'], 10, with_details=True)
+    want_rows, want_count, want_kth = oracle.topn(oracle_index_from_encoded(enc), 10)
+    assert np.array_equal(count, want_count)
+    assert np.array_equal(rows, want_rows)
+    assert np.array_equal(kth, want_kth)
+
+
 def _tiny_case(truth_sets, query_sets, n_vocab):
     """Hand-built index: column ids given directly, idf from document frequencies."""
     import math
