@@ -23,7 +23,7 @@ MAX_TITLE = 255
 
 # every symbol include/doppelspeller_b200.h declares (tests check that the library exports them all)
 EXPORTED_SYMBOLS = (
-    'ds_version', 'ds_last_error', 'ds_kernel_launches', 'ds_profile_begin', 'ds_profile_end', 'ds_profile_end_split',
+    'ds_version', 'ds_last_error', 'ds_kernel_launches', 'ds_profile_begin', 'ds_profile_end', 'ds_profile_end_split', 'ds_transform_titles',
     'ds_index_create', 'ds_index_destroy', 'ds_index_get_sums',
     'ds_topn', 'ds_topn_retained', 'ds_topn_local', 'ds_topn_merge', 'ds_topn_rescan',
     'ds_indel_ratio_u8', 'ds_indel_ratio_pairs', 'ds_levenshtein_ratio_pairs',
@@ -55,6 +55,7 @@ lib.ds_topn_retained.argtypes = [_i32]
 lib.ds_encode_max_vocab.restype = _i32
 lib.ds_encode_trigrams.argtypes = [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_i32),
                                    ctypes.POINTER(_i64), ctypes.POINTER(_i64), ctypes.c_int, _vp]
+lib.ds_transform_titles.argtypes = [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, ctypes.c_int, _vp]
 lib.ds_index_create.argtypes = [ctypes.POINTER(_vp), ctypes.c_int, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _i64, _vp]
 lib.ds_index_destroy.argtypes = [_vp]
 lib.ds_index_get_sums.argtypes = [_vp, _vp, _vp]
@@ -124,6 +125,12 @@ def current_stream():
     if not torch.cuda.is_available():
         return None
     return torch.cuda.current_stream().cuda_stream
+
+
+def current_device():
+    """ordinal of torch's current CUDA device (0 when no GPU is usable: the native call then reports DS_ERR_CUDA)"""
+    import torch
+    return torch.cuda.current_device() if torch.cuda.is_available() else 0
 
 
 def expect(array, dtype, name):

@@ -130,6 +130,66 @@ static int encode_side(Workspace &ws, const uint8_t *d_bytes, const int64_t *d_o
     return DS_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// f3: transform_title (common.py:20-47) for a batch of titles given as Unicode code points.
+//   unicodedata.normalize('NFD') + encode('ascii', 'ignore'): every code point contributes the ASCII
+//   characters of its canonical decomposition - at most one (table `ascii_of_cp`, built by the caller from
+//   its Unicode database; code points beyond the table contribute nothing) - then lower(), '-' -> ' ',
+//   keep [a-zA-Z0-9\s], collapse runs of ' ', strip(), remember the length, [:255].strip(), and left-pad
+//   with '0' to N_GRAMS = 3 characters when the remembered length is below 3.
+// One thread per title (a title is a few dozen characters); PASS 0 yields the lengths, PASS 1 the bytes.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool is_py_space(int c) {   // str.isspace() / regex \s over ASCII
+    return c == 32 || (c >= 9 && c <= 13) || (c >= 28 && c <= 31);
+}
+
+template <int PASS>
+__global__ void k_transform(const uint32_t *__restrict__ cps, const int64_t *__restrict__ offsets, int64_t n_titles,
+                            const uint8_t *__restrict__ ascii_of_cp, int table_len, int32_t *__restrict__ raw_len,
+                            int64_t *__restrict__ out_len, const int64_t *__restrict__ out_offsets, uint8_t *__restrict__ out) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_titles) return;
+    int limit = 0, pad = 0;
+    uint8_t *dst = nullptr;
+    if (PASS == 1) {
+        const int n = raw_len[t];
+        pad = n < 3 ? 3 - n : 0;
+        limit = (int)(out_offsets[t + 1] - out_offsets[t]) - pad;
+        dst = out + out_offsets[t];
+        for (int i = 0; i < pad; ++i) dst[i] = '0';
+        dst += pad;
+    }
+    int kept = 0;          // characters after the collapse and the left strip
+    int last_solid = 0;    // kept characters up to and including the last non-space one
+    int last_solid_255 = 0;
+    int prev = -1;
+    for (int64_t i = offsets[t]; i < offsets[t + 1]; ++i) {
+        const uint32_t cp = cps[i];
+        int c = cp < (uint32_t)table_len ? ascii_of_cp[cp] : 0;
+        if (c == 0) continue;
+        if (c >= 'A' && c <= 'Z') c += 32;
+        if (c == '-') c = ' ';
+        const bool space = is_py_space(c);
+        if (!(space || (c >= 'a' && c <= 'z') || (c >= '0' && c <= '9'))) continue;
+        if (c == ' ' && prev == ' ') continue;   // ' +' -> ' ' (other white space is kept as it is)
+        prev = c;
+        if (kept == 0 && space) continue;        // left strip
+        if (PASS == 1 && kept < limit) dst[kept] = (uint8_t)c;
+        ++kept;
+        if (!space) {
+            last_solid = kept;
+            if (kept <= 255) last_solid_255 = kept;
+        }
+    }
+    if (PASS == 0) {
+        const int n = last_solid;                                  // len(text) after strip()
+        const int text = n <= 255 ? n : last_solid_255;            // text[:255].strip()
+        raw_len[t] = n;
+        out_len[t] = n < 3 ? 3 : text;
+    }
+}
+
 }  // namespace ds
 
 using namespace ds;
@@ -251,6 +311,64 @@ int ds_encode_trigrams(const uint8_t *truth_bytes, const int64_t *truth_offsets,
     *out_n_vocab = n_vocab;
     *out_truth_nnz = truth_nnz;
     *out_query_nnz = query_nnz;
+    return ws.finish_outputs();
+}
+
+int ds_transform_titles(const uint32_t *codepoints, const int64_t *offsets, int64_t n_titles, const uint8_t *ascii_of_cp,
+                        int32_t table_len, uint8_t *out_bytes, int64_t *out_offsets, int32_t *out_raw_len, int device,
+                        void *stream_) {
+    if (n_titles < 0 || (n_titles > 0 && offsets == nullptr)) return fail(DS_ERR_BAD_ARG, "bad n_titles / offsets");
+    if (ascii_of_cp == nullptr || table_len < 128) return fail(DS_ERR_BAD_ARG, "ascii_of_cp must cover at least the ASCII range");
+    if (out_bytes == nullptr || out_offsets == nullptr) return fail(DS_ERR_BAD_ARG, "out_bytes / out_offsets is NULL");
+    int n_devices = 0;
+    if (cudaGetDeviceCount(&n_devices) != cudaSuccess || n_devices == 0) {
+        cudaGetLastError();
+        return fail(DS_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    DeviceGuard guard(device);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    Workspace ws(stream);
+    int64_t total = 0;
+    if (n_titles > 0) {
+        if (is_device_pointer(offsets)) {
+            DS_CUDA(cudaMemcpyAsync(&total, offsets + n_titles, 8, cudaMemcpyDeviceToHost, stream));
+            DS_CUDA(cudaStreamSynchronize(stream));
+        } else {
+            total = offsets[n_titles];
+        }
+    }
+    if (total < 0) return fail(DS_ERR_BAD_ARG, "offsets must be non-decreasing from 0");
+    const uint32_t *d_cps = nullptr;
+    const int64_t *d_off = nullptr;
+    const uint8_t *d_table = nullptr;
+    DS_CHECK(ws.stage_in(&d_cps, codepoints, (size_t)std::max<int64_t>(1, total)));
+    DS_CHECK(ws.stage_in(&d_off, offsets, (size_t)n_titles + 1));
+    DS_CHECK(ws.stage_in(&d_table, ascii_of_cp, (size_t)table_len));
+    uint8_t *d_out = nullptr;
+    int64_t *d_out_off = nullptr, *d_len = nullptr;
+    int32_t *d_raw = nullptr;
+    DS_CHECK(ws.stage_out(&d_out, out_bytes, (size_t)(total + 3 * n_titles + 1)));   // a title never grows beyond max(len, 3)
+    DS_CHECK(ws.stage_out(&d_out_off, out_offsets, (size_t)n_titles + 1));
+    DS_CHECK(ws.stage_out(&d_raw, out_raw_len, (size_t)n_titles));
+    if (d_raw == nullptr) DS_CHECK(ws.alloc(&d_raw, (size_t)std::max<int64_t>(1, n_titles)));
+    DS_CHECK(ws.alloc(&d_len, (size_t)n_titles + 1));
+    DS_CUDA(cudaMemsetAsync(d_len, 0, ((size_t)n_titles + 1) * 8, stream));
+    if (n_titles > 0) {
+        k_transform<0><<<(unsigned)ceil_div(n_titles, 128), 128, 0, stream>>>(d_cps, d_off, n_titles, d_table, table_len, d_raw, d_len,
+                                                                            nullptr, nullptr);
+        DS_LAUNCHED("k_transform");
+    }
+    size_t temp_bytes = 0;
+    DS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, d_len, d_out_off, (int)(n_titles + 1), stream));
+    unsigned char *temp = nullptr;
+    DS_CHECK(ws.alloc(&temp, temp_bytes));
+    DS_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, d_len, d_out_off, (int)(n_titles + 1), stream));
+    g_kernel_launches.fetch_add(1);
+    if (n_titles > 0) {
+        k_transform<1><<<(unsigned)ceil_div(n_titles, 128), 128, 0, stream>>>(d_cps, d_off, n_titles, d_table, table_len, d_raw, nullptr,
+                                                                            d_out_off, d_out);
+        DS_LAUNCHED("k_transform");
+    }
     return ws.finish_outputs();
 }
 

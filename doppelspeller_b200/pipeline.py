@@ -32,9 +32,14 @@ class CandidatePipeline:
     """Holds the truth side on the GPU (index, code table, word counts); `run(test_titles, top_n)` returns
     (rows int64[Q, top_n] descending truth rows, features float32[Q * top_n, 66]) as CUDA tensors."""
 
-    def __init__(self, truth_titles, device=0):
+    def __init__(self, truth_titles, device=0, raw=False):
+        """`raw=True`: the titles are raw input strings; common.transform_title (common.py:20-47) runs on the GPU first."""
         import torch
         self.device = torch.device('cuda', device)
+        if raw:
+            from . import common
+            with torch.cuda.device(self.device):
+                truth_titles = common.transform_titles(truth_titles)
         self.truth_titles = truth_titles
         codes, offsets = fe.encode_titles(truth_titles)
         self.truth_codes = torch.as_tensor(codes).to(self.device)
@@ -44,11 +49,16 @@ class CandidatePipeline:
         self.truth_table = (torch.as_tensor(raw).to(self.device), torch.as_tensor(raw_offsets).to(self.device))
         self._prematch_truth = None
 
-    def run(self, test_titles, top_n, with_prematch=False):
-        """-> (rows, count, features) or, with_prematch, (rows, count, features, ratios) where ratios int32[Q * top_n]
+    def run(self, test_titles, top_n, with_prematch=False, raw=False):
+        """`raw=True`: `test_titles` are raw input strings (transformed on the GPU first).
+        -> (rows, count, features) or, with_prematch, (rows, count, features, ratios) where ratios int32[Q * top_n]
         is Prediction._get_levenshtein_ratio of every (title, candidate) pair (predict.py:147-156, the input of the
         "very close match" selection :172-176)."""
         import torch
+        if raw:
+            from . import common
+            with torch.cuda.device(self.device):
+                test_titles = common.transform_titles(test_titles)
         enc = encode.encode_canonical_device(test_titles, None, device=self.device.index, truth_table=self.truth_table)
         index = TruthIndex(enc['t_ptr'], enc['t_cols'], enc['idf64'], device=self.device.index)
         rows, count = index.topn(enc['q_ptr'], enc['q_cols'], top_n)

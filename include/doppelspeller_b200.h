@@ -90,6 +90,26 @@ int ds_index_destroy(ds_index *index);
 int ds_index_get_sums(const ds_index *index, float *out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * ds_transform_titles  -  common.transform_title (common.py:20-47) for a batch of raw titles (SURVEY.md
+ * 8(f3)): NFD + ascii-ignore, lower(), '-' -> ' ', keep [a-zA-Z0-9\s], collapse runs of ' ', strip(),
+ * [:255].strip(), left-pad with '0' to 3 characters.
+ *   codepoints [offsets[n_titles]], offsets [n_titles+1]   the titles as Unicode code points (UTF-32)
+ *   ascii_of_cp [table_len]   for every code point below table_len the ASCII character of its canonical
+ *                        decomposition (0 = none; no code point has two); code points >= table_len are
+ *                        dropped.  The caller derives the table from its Unicode database
+ *                        (doppelspeller_b200/common.py builds it with `unicodedata`; 8,816 entries).
+ *   out_bytes [capacity offsets[n_titles] + 3 * n_titles + 1], out_offsets [n_titles+1]
+ *                        compact table of the transformed titles - the input format of ds_encode_trigrams and
+ *                        the ds_*_pairs entry points (letters / digits / spaces; other white space survives
+ *                        exactly where the reference keeps it)
+ *   out_raw_len [n_titles]   optional: len(text) before the [:255] cut (the reference logs a warning when it is
+ *                        below 3 or above 255, common.py:34-45)
+ * ------------------------------------------------------------------------------------------------- */
+int ds_transform_titles(const uint32_t *codepoints, const int64_t *offsets, int64_t n_titles, const uint8_t *ascii_of_cp,
+                        int32_t table_len, uint8_t *out_bytes, int64_t *out_offsets, int32_t *out_raw_len, int device,
+                        void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * ds_encode_trigrams  -  the host half of MatchMaker.__init__ on the GPU: titles ->
  * per-title trigram SETS (common.py:150-151) -> column ids -> document frequencies over the truth sets
  * (common.py:145-147) -> idf = log(N / df), query-only trigrams weighted with the maximum idf

@@ -317,3 +317,31 @@ def prematch_ratio(x, y, threshold=94):
     if ratio <= threshold:
         return levenshtein_token_sort_ratio(x, y)
     return ratio
+
+
+# ---------------------------------------------------------------------------------------------------
+# f3: transform_title (common.py:20-47), restated character by character (no regular expressions) so that
+# it is an independent check of both the reference's regex formulation and the CUDA state machine
+# ---------------------------------------------------------------------------------------------------
+def transform_title(title, n_grams=3, max_chars=255):
+    import unicodedata
+    kept = []
+    for ch in unicodedata.normalize('NFD', title):                      # common.py:25
+        if ord(ch) >= 128:                                              # .encode('ascii', 'ignore')  :26
+            continue
+        ch = ch.lower()                                                 # .lower()                    :26
+        if ch == '-':                                                   # .replace('-', ' ')          :26
+            ch = ' '
+        if ch.isalnum() or ch.isspace():                                # KEEP_REGEX [a-zA-Z0-9\s]    :28
+            kept.append(ch)
+    collapsed = []
+    for ch in kept:                                                     # SUBSTITUTE_REGEX ' +' -> ' ' :30
+        if ch == ' ' and collapsed and collapsed[-1] == ' ':
+            continue
+        collapsed.append(ch)
+    text = ''.join(collapsed).strip()                                   # .strip()                    :30
+    number_of_characters = len(text)                                    # :31
+    text = text[:max_chars].strip()                                     # :32
+    if number_of_characters < n_grams:                                  # :34-38
+        return text.rjust(n_grams, '0')
+    return text

@@ -43,6 +43,16 @@ def example_titles():
                 test_titles=[str(t) for t in raw['test_titles']], test_index=raw['test_index'])
 
 
+@pytest.fixture(scope='session')
+def golden_transform():
+    """(raw titles, reference transform_title outputs) minted by tests/golden/make_transform_golden.py"""
+    g = np.load(os.path.join(GOLDEN, 'transform_titles.npz'))
+    ib, io, ob, oo = g['in_bytes'], g['in_off'], g['out_bytes'], g['out_off']
+    titles = [ib[io[i]:io[i + 1]].tobytes().decode('utf-8', 'surrogatepass') for i in range(len(io) - 1)]
+    outputs = [ob[oo[i]:oo[i + 1]].tobytes().decode('latin-1') for i in range(len(oo) - 1)]
+    return titles, outputs
+
+
 def oracle_index_from_golden(g):
     """Finished oracle index from the golden fixture's explicit column ids / set order."""
     from oracle import oracle

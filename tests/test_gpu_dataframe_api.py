@@ -136,6 +136,19 @@ def test_candidate_pipeline_end_to_end(example_titles):
     assert np.array_equal(ratios, np.array([oracle.prematch_ratio(test[q], truth[t]) for q, t in zip(pairs_q, pairs_t)]))
 
 
+def test_candidate_pipeline_from_raw_titles(golden_transform):
+    """raw=True: transform_title on the GPU first; same candidates as the pipeline fed with the reference's outputs."""
+    from doppelspeller_b200.pipeline import CandidatePipeline
+    titles, outputs = golden_transform
+    keep = [i for i in range(4500) if 3 <= len(outputs[i]) <= 255 and set(outputs[i]) <= set(' abcdefghijklmnopqrstuvwxyz0123456789')]
+    truth_raw, truth_ref = [titles[i] for i in keep[:2500]], [outputs[i] for i in keep[:2500]]
+    test_raw, test_ref = [titles[i] for i in keep[2500:2700]], [outputs[i] for i in keep[2500:2700]]
+    rows_raw, count_raw, feats_raw = CandidatePipeline(truth_raw, raw=True).run(test_raw, 5, raw=True)
+    rows_ref, count_ref, feats_ref = CandidatePipeline(truth_ref).run(test_ref, 5)
+    assert np.array_equal(rows_raw.cpu().numpy(), rows_ref.cpu().numpy())
+    assert np.array_equal(feats_raw.cpu().numpy().view(np.uint32), feats_ref.cpu().numpy().view(np.uint32))
+
+
 def test_indexed_prematch_matches_per_pair_form(example_titles, golden_matchmaker):
     """The table + index form of the fuzzy pre-match (token sort once per title, everything on the GPU) against
     the per-pair form and the oracle."""

@@ -371,3 +371,20 @@ def test_randomised_shapes_against_oracle():
             truth[0] = [0]
         queries = [row(60) for _ in range(n_q)]
         _check_against_oracle(_tiny_case(truth, queries, n_vocab), k)
+
+
+# ------------------------------------------------------------------ f3: transform_title
+def test_transform_titles_match_reference(golden_transform):
+    """ds_transform_titles (k_transform) against the reference's transform_title outputs: host and device tables."""
+    import torch
+    from doppelspeller_b200 import common
+    titles, outputs = golden_transform
+    assert common.transform_titles(titles) == outputs
+    assert common.transform_title(titles[4500]) == outputs[4500]
+    out, off, raw = common.transform_titles_table(titles, device=torch.cuda.current_device(), warn=False)
+    out, off = out.cpu().numpy(), off.cpu().numpy()
+    blob = out.tobytes().decode('latin-1')
+    assert [blob[off[i]:off[i + 1]] for i in range(len(titles))] == outputs
+    assert common.transform_titles([]) == []
+    # raw_len = len(text) before the [:255] cut (drives the reference's two warnings)
+    assert int(raw[titles.index('x' * 256)]) == 256 and int(raw[titles.index('--')]) == 0

@@ -67,3 +67,16 @@ def test_synthetic_generator_is_deterministic_and_normalised():
     for title in a + t1 + synthetic.generate_long_titles(20, seed=3):
         assert 3 <= len(title) <= 255 and title == ' '.join(title.split())
         assert set(title) <= set(' abcdefghijklmnopqrstuvwxyz0123456789')
+
+
+def test_ascii_of_codepoint_table():
+    """The table handed to ds_transform_titles: NFD + ascii-ignore per code point (common.py:25-26)."""
+    import unicodedata
+    from doppelspeller_b200 import common
+    table = common.ascii_of_codepoint_table()
+    assert table.dtype == np.uint8 and table.shape[0] == 0x2270
+    assert all(table[c] == c for c in range(1, 128)) and table[0] == 0
+    for ch, want in (('é', 'e'), ('Å', 'A'), ('ñ', 'n'), ('ø', ''), ('ß', ''), ('\u212a', 'K'), ('≠', '='), ('ﬁ', ''), ('株', '')):
+        cp = ord(ch)
+        got = chr(table[cp]) if cp < table.shape[0] and table[cp] else ''
+        assert got == want == unicodedata.normalize('NFD', ch).encode('ascii', 'ignore').decode()

@@ -87,3 +87,12 @@ def test_levenshtein_ratio_known_answers():
     assert oracle.levenshtein_ratio('abcd', 'abcx') == 75
     assert oracle.levenshtein_token_sort_ratio('bv coolblue', 'coolblue bv') == 100
     assert oracle.prematch_ratio('a' * 10, 'a' * 30) == 0                        # length pre-filter (predict.py:150)
+
+
+def test_transform_title_matches_reference(golden_transform):
+    """common.py:20-47 on 7,016 raw titles (example data + seeded accents / white space / length edge cases) and the
+    reference's own test vector (doppelspeller/tests/test_common.py:16-19)."""
+    titles, outputs = golden_transform
+    assert [oracle.transform_title(t) for t in titles] == outputs
+    assert oracle.transform_title('''LKJblksd skjasl dfkjf &* 8*&&&8 GGdjsdkj--sdsd-"sdi..//' d'  k   bkjh77_asda33''') == \
+        'lkjblksd skjasl dfkjf 88 ggdjsdkj sdsd sdi d k bkjh77asda33'

@@ -119,3 +119,22 @@ def test_reference_golden_tests_still_hold(ref):
     # the reference's own three tests (doppelspeller/tests/test_common.py:16-28)
     title = '''LKJblksd skjasl dfkjf &* 8*&&&8 GGdjsdkj--sdsd-"sdi..//' d'  k   bkjh77_asda33'''
     assert ref.common.transform_title(title) == 'lkjblksd skjasl dfkjf 88 ggdjsdkj sdsd sdi d k bkjh77asda33'
+
+
+def test_transform_title_random_unicode(ref):
+    """oracle.transform_title against the reference's regex formulation on random code point soup."""
+    import logging
+    logging.disable(logging.CRITICAL)
+    try:
+        rng = np.random.default_rng(77)
+        ranges = [(0, 0x80), (0x80, 0x250), (0x300, 0x370), (0x1E00, 0x2300), (0x3000, 0x3100), (0xFB00, 0xFB10), (0x1F600, 0x1F610)]
+        for _ in range(1500):
+            n = int(rng.integers(0, 80))
+            chars = []
+            for _ in range(n):
+                lo, hi = ranges[int(rng.integers(len(ranges)))]
+                chars.append(chr(int(rng.integers(lo, hi))))
+            title = ''.join(chars)
+            assert oracle.transform_title(title) == ref.common.transform_title(title), repr(title)
+    finally:
+        logging.disable(logging.NOTSET)
