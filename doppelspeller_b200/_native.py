@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, '_lib', 'libdoppelspeller_b200.so')
+# DOPPELSPELLER_B200_LIB: explicit path of the built library (deployments that keep it elsewhere, kernel A/B builds)
+LIB_PATH = os.environ.get('DOPPELSPELLER_B200_LIB') or os.path.join(_HERE, '_lib', 'libdoppelspeller_b200.so')
 
 DS_OK = 0
 DS_FLAG_RESCAN = 1
