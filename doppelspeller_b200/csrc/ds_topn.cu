@@ -11,7 +11,12 @@
 //            in descending row order.
 //   mx       doppelspeller/match_maker.py:197     python sum() over the ascending column ids
 //
-// Design (B200): the truth rows live in HBM as 8-byte chunks of four ascending u16 column ids
+// Design (B200): two forms of the same scan.  k_post (the bulk of the rows) walks the inverted index: per
+// block of 2,048 row positions and column id the rows holding the column; one warp = one query x a run of
+// blocks, one float32 accumulator per row in shared memory, the query's columns walked in ascending id
+// order (see the kernel).  k_scan (the first 4,096 rows that seed the thresholds, the fixed-threshold and
+// bounded-memory fallbacks, small or non-monotone indexes) streams the rows themselves: they live in HBM as
+// 8-byte chunks of four ascending u16 column ids
 // (sentinel padded); a CTA owns a tile of up to 32 queries whose columns are scattered once into a
 // shared-memory direct map  column id -> slot -> (32-bit query mask, idf32)  and then streams truth
 // rows, one row per thread, with 32 register accumulators.  Adding the row's columns in ascending
