@@ -71,6 +71,22 @@ def test_negative_weight_keeps_the_dense_scan():
     assert np.array_equal(kth, want_kth)
 
 
+def test_long_title_index_keeps_the_dense_scan():
+    """Blocks of 2,048 long titles hold more than 65,535 postings (the 16-bit segment offsets of the posting form):
+    such an index stays on the dense row scan; queries with more than 32 trigrams go through both forms elsewhere."""
+    from doppelspeller_b200 import encode, synthetic
+    from oracle import oracle
+    truth = synthetic.generate_long_titles(5000, seed=71)
+    test, _ = synthetic.generate_test_titles(truth, 120, seed=72)
+    enc = encode.encode_canonical(test, truth)
+    assert np.diff(enc['t_ptr'])[:2048].sum() > 65535
+    rows, count, kth, _ = _match_maker(enc, 10)._index.topn(enc['q_ptr'], enc['q_cols'], 10, with_details=True)
+    want_rows, want_count, want_kth = oracle.topn(oracle_index_from_encoded(enc), 10)
+    assert np.array_equal(count, want_count)
+    assert np.array_equal(rows, want_rows)
+    assert np.array_equal(kth, want_kth)
+
+
 def _tiny_case(truth_sets, query_sets, n_vocab):
     """Hand-built index: column ids given directly, idf from document frequencies."""
     import math
