@@ -62,6 +62,7 @@ constexpr int SORT_BLOCK = 4096;    // rows are length-sorted inside blocks of t
 constexpr int POST_ROWS = 2048;     // row positions per posting block = f32 accumulators per warp in k_post (8 KB)
 constexpr int POST_WARPS = 13;      // warps per CTA; two CTAs (26 warps, 213 KB of accumulators) per SM
 constexpr int POST_LIST = 64;       // per warp: rows of the swept block waiting for the full filter
+// tuning knobs of k_post, overridable at build time (-DDS_POST_...=n) for A/B builds; defaults = measured best on C3
 #ifndef DS_POST_RUN
 #define DS_POST_RUN 8
 #endif
@@ -71,8 +72,8 @@ constexpr int POST_LIST = 64;       // per warp: rows of the swept block waiting
 #ifndef DS_POST_TASKS
 #define DS_POST_TASKS 8
 #endif
-constexpr int POST_RUN = DS_POST_RUN;         // consecutive posting blocks per warp task (the query's columns are loaded once)
-constexpr int POST_DEPTH = DS_POST_DEPTH;       // posting pieces (<= 64 postings each) in flight per warp
+constexpr int POST_RUN = DS_POST_RUN;      // consecutive posting blocks per warp task (the query's columns are loaded once)
+constexpr int POST_DEPTH = DS_POST_DEPTH;  // posting pieces (<= 64 postings each) in flight per warp
 constexpr int POST_GROUPS = POST_ROWS / 128;   // the block sweep takes 128 rows at a time (<= 32 groups: one lane each)
 constexpr int POST_CTAS = POST_ROWS <= 2048 ? 2 : 1;
 typedef std::conditional<POST_ROWS <= 2048, uint16_t, uint32_t>::type post_off_t;   // segment offsets inside a block
@@ -1188,7 +1189,7 @@ static int launch_post(const Index &ix, cudaStream_t stream, PostParams pp, int 
     const long long wanted_tasks = (long long)148 * 2 * POST_WARPS * 2;
     pp.run_len = (int)std::min<long long>(POST_RUN, std::max<long long>(1, (long long)(s1 - s0) * pp.n_batch / wanted_tasks));
     pp.n_tasks = ceil_div(s1 - s0, pp.run_len) * (long long)pp.n_batch;
-    // tasks are handed out warp by warp inside a CTA; several per warp level the very uneven task lengths
+    // tasks are handed out warp by warp inside a CTA; DS_POST_TASKS per warp level the very uneven task lengths
     pp.tasks_per_cta = (int)std::min<long long>(POST_WARPS * DS_POST_TASKS, std::max<long long>(POST_WARPS, ceil_div(pp.n_tasks, (long long)148 * 2 * 2)));
     const long long ctas = ceil_div(pp.n_tasks, (long long)pp.tasks_per_cta);
     if (ctas > INT32_MAX) return fail(DS_ERR_UNSUPPORTED, "too many posting tasks in one launch");
