@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = (
     'ds_topn', 'ds_topn_retained', 'ds_topn_local', 'ds_topn_merge', 'ds_topn_rescan',
     'ds_indel_ratio_u8', 'ds_indel_ratio_pairs', 'ds_levenshtein_ratio_pairs',
     'ds_construct_features', 'ds_construct_features_pairs',
-    'ds_encode_max_vocab', 'ds_encode_trigrams',
+    'ds_encode_max_vocab', 'ds_encode_trigrams', 'ds_gbdt_predict',
 )
 
 
@@ -57,6 +57,7 @@ lib.ds_encode_max_vocab.restype = _i32
 lib.ds_encode_trigrams.argtypes = [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_i32),
                                    ctypes.POINTER(_i64), ctypes.POINTER(_i64), ctypes.c_int, _vp]
 lib.ds_transform_titles.argtypes = [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, ctypes.c_int, _vp]
+lib.ds_gbdt_predict.argtypes = [_vp, _i64, _i32, _vp, _vp, _i32, ctypes.c_float, _i32, _vp, _vp]
 lib.ds_index_create.argtypes = [ctypes.POINTER(_vp), ctypes.c_int, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _i64, _vp]
 lib.ds_index_destroy.argtypes = [_vp]
 lib.ds_index_get_sums.argtypes = [_vp, _vp, _vp]

@@ -1,0 +1,156 @@
+// ds_gbdt.cu - f4: gradient-boosted tree inference over the [P, 66] feature matrix, on the device.
+//
+// Replaces `self.model.predict(xgb.DMatrix(features), ...)` of /root/reference/doppelspeller/predict.py:229-233
+// (model trained by train.py:99-121: xgboost==0.90, requirements.txt:8; max_depth 5, <= 1000 rounds, objective
+// reg:logistic).  xgboost is a third-party dependency that is neither vendored in the reference nor installed
+// here, so its published prediction algorithm (xgboost 0.90 src/predictor/cpu_predictor.cc `PredValue`,
+// include/xgboost/tree_model.h `GetNext`, src/objective/regression_loss.h `LogisticRegression::PredTransform`)
+// is restated - parity with a real model file is unpinned:
+//   per row:  psum = 0.0f; for every tree in boosting order: walk from the root - a NaN feature takes the node's
+//             default child, otherwise `feature < split ? yes : no` (strict, float32) - and psum += leaf (float32);
+//             margin = base_margin + psum;  reg:logistic / binary:logistic: 1 / (1 + exp(-margin)) in float32.
+//
+// One thread per row.  The trees of a model (<= 1000 x <= 63 nodes x 16 B = 1 MB) are streamed through shared
+// memory in chunks shared by the 256 rows of a CTA; a row's 264 bytes of features stay L1 resident.
+#include "ds_common.cuh"
+
+namespace ds {
+
+constexpr int GBDT_THREADS = 256;
+constexpr int GBDT_CHUNK_NODES = 2560;   // 40 KB of nodes per chunk (static shared memory)
+
+static_assert(sizeof(ds_gbdt_node) == 16, "ds_gbdt_node must be 16 bytes");
+
+__global__ void __launch_bounds__(GBDT_THREADS) k_gbdt_predict(const float *__restrict__ features, int64_t n_rows, int n_features,
+                                                               const ds_gbdt_node *__restrict__ nodes,
+                                                               const int32_t *__restrict__ tree_offsets, int n_trees, float base_margin,
+                                                               int transform, float *__restrict__ out) {
+    __shared__ uint4 s_nodes[GBDT_CHUNK_NODES];
+    __shared__ int s_first_tree, s_last_tree;
+    const int64_t row = (int64_t)blockIdx.x * GBDT_THREADS + threadIdx.x;
+    const float *x = features + (row < n_rows ? row : 0) * (int64_t)n_features;
+    float psum = 0.0f;
+    int tree = 0;
+    while (tree < n_trees) {
+        // the next run of whole trees that fits the chunk (a single tree larger than the chunk is walked from global memory)
+        if (threadIdx.x == 0) {
+            int last = tree;
+            const int first_node = tree_offsets[tree];
+            while (last < n_trees && tree_offsets[last + 1] - first_node <= GBDT_CHUNK_NODES) ++last;
+            s_first_tree = tree;
+            s_last_tree = last;
+        }
+        __syncthreads();
+        const int first = s_first_tree, last = s_last_tree;
+        if (last == first) {
+            const ds_gbdt_node *t = nodes + tree_offsets[first];
+            int node = 0;
+            ds_gbdt_node nd = t[0];
+            while (nd.feature >= 0) {
+                const float v = x[nd.feature];
+                node = isnan(v) ? nd.missing : (v < nd.value ? nd.yes : nd.no);
+                nd = t[node];
+            }
+            psum = __fadd_rn(psum, nd.value);
+            tree = first + 1;
+            __syncthreads();
+            continue;
+        }
+        const int node0 = tree_offsets[first], node1 = tree_offsets[last];
+        const uint4 *src = reinterpret_cast<const uint4 *>(nodes + node0);
+        for (int i = threadIdx.x; i < node1 - node0; i += GBDT_THREADS) s_nodes[i] = src[i];
+        __syncthreads();
+        if (row < n_rows) {
+            for (int t = first; t < last; ++t) {
+                const int root = tree_offsets[t] - node0;
+                uint4 raw = s_nodes[root];
+                while ((int)raw.x >= 0) {
+                    const float v = x[raw.x];
+                    const int yes = raw.z & 0xffff, no = raw.z >> 16, missing = raw.w & 0xffff;
+                    const int next = isnan(v) ? missing : (v < __uint_as_float(raw.y) ? yes : no);
+                    raw = s_nodes[root + next];
+                }
+                psum = __fadd_rn(psum, __uint_as_float(raw.y));
+            }
+        }
+        tree = last;
+        __syncthreads();
+    }
+    if (row < n_rows) {
+        float margin = __fadd_rn(base_margin, psum);
+        if (transform == DS_GBDT_LOGISTIC) margin = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-margin)));
+        out[row] = margin;
+    }
+}
+
+}  // namespace ds
+
+using namespace ds;
+
+extern "C" {
+
+int ds_gbdt_predict(const float *features, int64_t n_rows, int32_t n_features, const ds_gbdt_node *nodes,
+                    const int32_t *tree_offsets, int32_t n_trees, float base_margin, int32_t transform, float *out,
+                    void *stream_) {
+    if (n_rows < 0 || n_features < 1 || n_trees < 0) return fail(DS_ERR_BAD_ARG, "bad n_rows / n_features / n_trees");
+    if (n_rows > 0 && (features == nullptr || out == nullptr)) return fail(DS_ERR_BAD_ARG, "features / out is NULL");
+    if (n_trees > 0 && (nodes == nullptr || tree_offsets == nullptr)) return fail(DS_ERR_BAD_ARG, "nodes / tree_offsets is NULL");
+    if (transform != DS_GBDT_MARGIN && transform != DS_GBDT_LOGISTIC) return fail(DS_ERR_BAD_ARG, "unknown transform %d", transform);
+    int n_devices = 0;
+    if (cudaGetDeviceCount(&n_devices) != cudaSuccess || n_devices == 0) {
+        cudaGetLastError();
+        return fail(DS_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (n_rows == 0) return DS_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    Workspace ws(stream);
+    // validate the model on the host when it is host resident (child indexes inside their tree, features in range)
+    std::vector<int32_t> h_offsets((size_t)n_trees + 1, 0);
+    if (n_trees > 0) {
+        if (is_device_pointer(tree_offsets)) {
+            DS_CUDA(cudaMemcpyAsync(h_offsets.data(), tree_offsets, ((size_t)n_trees + 1) * 4, cudaMemcpyDeviceToHost, stream));
+            DS_CUDA(cudaStreamSynchronize(stream));
+        } else {
+            memcpy(h_offsets.data(), tree_offsets, ((size_t)n_trees + 1) * 4);
+        }
+        if (h_offsets[0] != 0) return fail(DS_ERR_BAD_ARG, "tree_offsets must start at 0");
+        for (int t = 0; t < n_trees; ++t) {
+            const int64_t size = (int64_t)h_offsets[(size_t)t + 1] - h_offsets[(size_t)t];
+            if (size < 1 || size > 65535) return fail(DS_ERR_BAD_ARG, "tree %d has %lld nodes (1..65535 allowed)", t, (long long)size);
+        }
+        if (!is_device_pointer(nodes)) {
+            for (int t = 0; t < n_trees; ++t) {
+                const int size = h_offsets[(size_t)t + 1] - h_offsets[(size_t)t];
+                const ds_gbdt_node *tree = nodes + h_offsets[(size_t)t];
+                for (int i = 0; i < size; ++i) {
+                    if (tree[i].feature < 0) continue;
+                    if (tree[i].feature >= n_features || tree[i].yes >= size || tree[i].no >= size || tree[i].missing >= size ||
+                        tree[i].yes <= i || tree[i].no <= i || tree[i].missing <= i)
+                        return fail(DS_ERR_BAD_ARG, "tree %d node %d: feature or child index out of range (children must follow their parent)", t, i);
+                }
+            }
+        }
+    }
+    const int n_nodes = h_offsets[(size_t)n_trees];
+    const float *d_features = nullptr;
+    const ds_gbdt_node *d_nodes = nullptr;
+    const int32_t *d_offsets = nullptr;
+    float *d_out = nullptr;
+    DS_CHECK(ws.stage_in(&d_features, features, (size_t)n_rows * n_features));
+    DS_CHECK(ws.stage_in(&d_nodes, nodes, (size_t)std::max(1, n_nodes)));
+    DS_CHECK(ws.stage_in(&d_offsets, tree_offsets, (size_t)n_trees + 1));
+    DS_CHECK(ws.stage_out(&d_out, out, (size_t)n_rows));
+    const int32_t zero = 0;
+    if (n_trees == 0) {
+        int32_t *d_zero = nullptr;
+        DS_CHECK(ws.alloc(&d_zero, 1));
+        DS_CUDA(cudaMemcpyAsync(d_zero, &zero, 4, cudaMemcpyHostToDevice, stream));
+        d_offsets = d_zero;
+    }
+    k_gbdt_predict<<<(unsigned)ceil_div(n_rows, GBDT_THREADS), GBDT_THREADS, 0, stream>>>(d_features, n_rows, n_features, d_nodes, d_offsets,
+                                                                                       n_trees, base_margin, transform, d_out);
+    DS_LAUNCHED("k_gbdt_predict");
+    return ws.finish_outputs();
+}
+
+}  // extern "C"

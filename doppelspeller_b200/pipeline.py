@@ -79,3 +79,31 @@ class CandidatePipeline:
         ratios = predict.get_levenshtein_ratios_indexed(predict.PrematchTables(test_titles, device=self.device.index),
                                                         self._prematch_truth, title_index, truth_index)
         return rows, count, features, ratios
+
+    def predict(self, test_titles, top_n, model, raw=False):
+        """Prediction.generate_test_predictions after the exact-match join (predict.py:286-219,229-252), device resident up
+        to the final selection: candidates -> "very close" matches by the fuzzy ratio cascade (ratio > 94, the maximum of
+        its title, attained once: :158-176) -> for the remaining titles the model's probability over the 66 features
+        (`model`: gbdt.GbdtModel) > 0.9, the maximum of its title, attained once (:242-249).
+        -> dict(rows int64[Q, top_n], match_row int64[Q] (truth row or -1), match_kind uint8[Q] (0 none, 1 close match,
+        2 model), prediction float32[Q] (1.0 for close matches, the model's probability otherwise))."""
+        from . import gbdt, predict
+        rows, count, features, ratios = self.run(test_titles, top_n, with_prematch=True, raw=raw)
+        n_q = rows.shape[0]
+        probabilities = model.predict(features).cpu().numpy()
+        rows_host, ratios_host = rows.cpu().numpy(), ratios.cpu().numpy()
+        test_index = np.repeat(np.arange(n_q), top_n)
+        valid = (rows_host.reshape(-1) >= 0)
+        match_row = np.full(n_q, -1, dtype=np.int64)
+        match_kind = np.zeros(n_q, dtype=np.uint8)
+        prediction = np.zeros(n_q, dtype=np.float32)
+        close = predict.select_close_matches(test_index, np.where(valid, ratios_host, 0))
+        match_row[test_index[close]] = rows_host.reshape(-1)[close]
+        match_kind[test_index[close]] = 1
+        prediction[test_index[close]] = 1.0
+        open_pairs = valid & (match_kind[test_index] == 0)                       # predict.py:176: titles matched so far drop out
+        chosen = gbdt.select_model_matches(test_index, np.where(open_pairs, probabilities, -1.0))
+        match_row[test_index[chosen]] = rows_host.reshape(-1)[chosen]
+        match_kind[test_index[chosen]] = 2
+        prediction[test_index[chosen]] = probabilities[chosen]
+        return dict(rows=rows, match_row=match_row, match_kind=match_kind, prediction=prediction)

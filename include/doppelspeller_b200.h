@@ -222,6 +222,30 @@ int ds_construct_features_pairs(const uint8_t *bytes_a, const int64_t *offsets_a
                                 uint8_t space_code, uint32_t n_truth, int64_t n_pairs, float *out,
                                 void *stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * ds_gbdt_predict  -  replaces `model.predict(xgb.DMatrix(features))` (predict.py:229-233):
+ * inference of a gradient-boosted tree ensemble (train.py:99-121: xgboost 0.90, depth <= 5, <= 1000 rounds)
+ * over the float32 feature matrix.  Per row: psum = 0; for every tree in boosting order walk from node 0 -
+ * NaN feature -> `missing` child, else feature < value (strict) ? `yes` : `no` - and psum += leaf value
+ * (float32); margin = base_margin + psum; DS_GBDT_LOGISTIC applies 1 / (1 + exp(-margin)) in float32
+ * (reg:logistic / binary:logistic).  Children are node indexes INSIDE their tree and follow their parent.
+ *   features [n_rows, n_features] float32 row major; nodes [tree_offsets[n_trees]]; tree_offsets [n_trees+1]
+ *   base_margin: logit(base_score) for the logistic objectives (0 for the default base_score 0.5)
+ *   out [n_rows] float32
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct ds_gbdt_node {
+    int32_t feature;    /* column of the feature matrix this node tests; -1 = leaf */
+    float value;        /* split threshold, or the leaf's weight */
+    uint16_t yes, no;   /* children taken when feature < value / otherwise */
+    uint16_t missing;   /* child taken when the feature is NaN (xgboost's default direction) */
+    uint16_t reserved;
+} ds_gbdt_node;
+#define DS_GBDT_MARGIN 0
+#define DS_GBDT_LOGISTIC 1
+int ds_gbdt_predict(const float *features, int64_t n_rows, int32_t n_features, const ds_gbdt_node *nodes,
+                    const int32_t *tree_offsets, int32_t n_trees, float base_margin, int32_t transform, float *out,
+                    void *stream);
+
 #ifdef __cplusplus
 }
 #endif

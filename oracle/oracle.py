@@ -345,3 +345,36 @@ def transform_title(title, n_grams=3, max_chars=255):
     if number_of_characters < n_grams:                                  # :34-38
         return text.rjust(n_grams, '0')
     return text
+
+
+# ---------------------------------------------------------------------------------------------------
+# f4: gradient-boosted tree inference.  xgboost==0.90 (requirements.txt:8) is a third-party dependency absent from
+# /root/reference; its published CPU prediction path is restated (src/predictor/cpu_predictor.cc PredValue:
+# psum = 0.0f; psum += leaf of every tree in order; include/xgboost/tree_model.h GetNext: missing -> default child,
+# else fvalue < split_cond ? left : right; src/objective/regression_loss.h: sigmoid in float32).  Parity unpinned.
+# ---------------------------------------------------------------------------------------------------
+def gbdt_predict(features, nodes, tree_offsets, base_margin=0.0, logistic=True):
+    """features float32 [n, f]; nodes: structured array with fields feature/value/yes/no/missing (children relative to
+    their tree's first node); returns float32 [n]."""
+    x = np.ascontiguousarray(features, dtype=np.float32)
+    n = x.shape[0]
+    psum = np.zeros(n, dtype=np.float32)
+    rows = np.arange(n)
+    for t in range(len(tree_offsets) - 1):
+        tree = nodes[tree_offsets[t]:tree_offsets[t + 1]]
+        at = np.zeros(n, dtype=np.int64)
+        while True:
+            feature = tree['feature'][at]
+            active = feature >= 0
+            if not active.any():
+                break
+            value = x[rows, np.where(active, feature, 0)]
+            with np.errstate(invalid='ignore'):
+                go = np.where(np.isnan(value), tree['missing'][at], np.where(value < tree['value'][at], tree['yes'][at], tree['no'][at]))
+            at = np.where(active, go, at)
+        psum = (psum + tree['value'][at]).astype(np.float32)
+    margin = (np.float32(base_margin) + psum).astype(np.float32)
+    if not logistic:
+        return margin
+    with np.errstate(over='ignore'):
+        return (np.float32(1.0) / (np.float32(1.0) + np.exp(-margin, dtype=np.float32))).astype(np.float32)

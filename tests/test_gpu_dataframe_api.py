@@ -149,6 +149,47 @@ def test_candidate_pipeline_from_raw_titles(golden_transform):
     assert np.array_equal(feats_raw.cpu().numpy().view(np.uint32), feats_ref.cpu().numpy().view(np.uint32))
 
 
+def test_pipeline_predict_follows_reference_selection(example_titles):
+    """candidates -> close-match cascade -> model probabilities -> per-title selection, against a host restatement of
+    predict.py:158-176,242-249 fed with oracle quantities."""
+    from doppelspeller_b200 import gbdt
+    from doppelspeller_b200 import feature_engineering as fe
+    from doppelspeller_b200.pipeline import CandidatePipeline, truth_word_counts
+    from oracle import oracle
+    from tests.test_gpu_parity import _random_forest
+    truth, test = example_titles['truth_titles'], example_titles['test_titles'][:400]
+    k = 10
+    rng = np.random.default_rng(5)
+    trees = _random_forest(rng, 60, 66, 4)
+    for tree in trees:                           # thresholds in the range of the ratio features so that the trees discriminate
+        for i, (feature, value, yes, no, missing) in enumerate(tree):
+            if feature >= 0:
+                tree[i] = (int(rng.integers(4, 21)), float(np.float32(rng.uniform(20, 100))), yes, no, missing)
+    model = gbdt.GbdtModel.from_trees(trees, base_margin=1.0)
+    got = CandidatePipeline(truth).predict(test, k, model)
+    rows = got['rows'].cpu().numpy()
+    pairs_q, pairs_t = np.repeat(np.arange(len(test)), k), rows.reshape(-1)
+    la = np.array([len(test[q]) for q in pairs_q], np.uint8)
+    lb = np.array([len(truth[t]) for t in pairs_t], np.uint8)
+    a = np.vstack([fe.encode_title(test[q]) for q in pairs_q])
+    b = np.vstack([fe.encode_title(truth[t]) for t in pairs_t])
+    feats = oracle.construct_features(la, lb, a, b, truth_word_counts(truth)[pairs_t], fe.SPACE_CODE, len(truth))
+    probabilities = oracle.gbdt_predict(feats, model.nodes, model.tree_offsets, model.base_margin)
+    ratios = np.array([oracle.prematch_ratio(test[q], truth[t]) for q, t in zip(pairs_q, pairs_t)])
+    kinds = []
+    for q in range(len(test)):
+        r, pr, tr = ratios[q * k:(q + 1) * k], probabilities[q * k:(q + 1) * k], rows[q]
+        if r.max() > 94 and (r == r.max()).sum() == 1:
+            assert got['match_kind'][q] == 1 and got['match_row'][q] == tr[r.argmax()] and got['prediction'][q] == 1.0
+        elif pr.max() > 0.9 and (pr == pr.max()).sum() == 1 and abs(pr.max() - 0.9) > 1e-5:
+            assert got['match_kind'][q] == 2 and got['match_row'][q] == tr[pr.argmax()]
+            assert np.isclose(got['prediction'][q], pr.max(), rtol=1e-6)
+        elif abs(pr.max() - 0.9) > 1e-5 and (pr == pr.max()).sum() == 1:
+            assert got['match_kind'][q] == 0 and got['match_row'][q] == -1
+        kinds.append(int(got['match_kind'][q]))
+    assert kinds.count(1) > 20 and kinds.count(2) > 5 and kinds.count(0) > 5
+
+
 def test_indexed_prematch_matches_per_pair_form(example_titles, golden_matchmaker):
     """The table + index form of the fuzzy pre-match (token sort once per title, everything on the GPU) against
     the per-pair form and the oracle."""

@@ -404,3 +404,47 @@ def test_transform_titles_match_reference(golden_transform):
     assert common.transform_titles([]) == []
     # raw_len = len(text) before the [:255] cut (drives the reference's two warnings)
     assert int(raw[titles.index('x' * 256)]) == 256 and int(raw[titles.index('--')]) == 0
+
+
+# ------------------------------------------------------------------ f4: boosted-tree inference
+def _random_forest(rng, n_trees, n_features, max_depth):
+    trees = []
+    for _ in range(n_trees):
+        tree, frontier = [], [(0, 0)]
+        nodes = {0: None}
+        next_id = 1
+        while frontier:
+            node, depth = frontier.pop(0)
+            if depth < max_depth and rng.random() < 0.8:
+                yes, no = next_id, next_id + 1
+                next_id += 2
+                nodes[node] = (int(rng.integers(n_features)), float(np.float32(rng.normal(0, 40))), yes, no, yes if rng.random() < 0.5 else no)
+                frontier += [(yes, depth + 1), (no, depth + 1)]
+            else:
+                nodes[node] = (-1, float(np.float32(rng.normal(0, 0.3))), 0, 0, 0)
+        for i in range(next_id):
+            tree.append(nodes[i])
+        trees.append(tree)
+    return trees
+
+
+@pytest.mark.parametrize('n_trees,max_depth', [(300, 5), (1000, 5), (3, 12), (0, 1)])
+def test_gbdt_predict_matches_oracle(n_trees, max_depth):
+    import torch
+    from doppelspeller_b200 import gbdt
+    from oracle import oracle
+    rng = np.random.default_rng(100 + n_trees)
+    model = gbdt.GbdtModel.from_trees(_random_forest(rng, n_trees, 66, max_depth), base_margin=-0.4, transform=gbdt.LOGISTIC)
+    x = rng.normal(0, 50, size=(20011, 66)).astype(np.float32)
+    x[rng.random(x.shape) < 0.08] = np.nan
+    x[rng.random(x.shape) < 0.01] = np.inf
+    x[:, 5] = np.round(x[:, 5])                      # values that land exactly on thresholds exercise the strict `<`
+    want = oracle.gbdt_predict(x, model.nodes, model.tree_offsets, model.base_margin, logistic=True)
+    got = model.predict(x)
+    assert np.allclose(got, want, rtol=1e-6, atol=0)
+    got_dev = model.predict(torch.as_tensor(x).cuda()).cpu().numpy()
+    assert np.array_equal(got_dev.view(np.uint32), got.view(np.uint32))
+    margin_model = gbdt.GbdtModel(model.nodes, model.tree_offsets, model.base_margin, gbdt.MARGIN)
+    want_margin = oracle.gbdt_predict(x, model.nodes, model.tree_offsets, model.base_margin, logistic=False)
+    assert np.array_equal(margin_model.predict(x).view(np.uint32), want_margin.view(np.uint32))   # float32 sums: bit exact
+

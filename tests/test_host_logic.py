@@ -80,3 +80,30 @@ def test_ascii_of_codepoint_table():
         cp = ord(ch)
         got = chr(table[cp]) if cp < table.shape[0] and table[cp] else ''
         assert got == want == unicodedata.normalize('NFD', ch).encode('ascii', 'ignore').decode()
+
+
+def test_gbdt_dump_parser_and_oracle_semantics():
+    """xgboost JSON dump -> flat trees (children after their parent), and the restated prediction rule: strict `<`,
+    NaN -> the `missing` child, float32 sum in tree order, sigmoid."""
+    from doppelspeller_b200 import gbdt
+    from oracle import oracle
+    dump = ['{"nodeid": 0, "depth": 0, "split": "f2", "split_condition": 0.5, "yes": 1, "no": 2, "missing": 2, "children": ['
+            '{"nodeid": 1, "leaf": -0.25}, {"nodeid": 2, "depth": 1, "split": "f0", "split_condition": 3, "yes": 3, "no": 4, '
+            '"missing": 3, "children": [{"nodeid": 3, "leaf": 0.5}, {"nodeid": 4, "leaf": 1.5}]}]}',
+            '{"nodeid": 0, "leaf": 0.125}']
+    model = gbdt.GbdtModel.from_xgboost_dump(dump, base_score=0.5, objective='reg:logistic')
+    assert model.n_trees == 2 and model.tree_offsets.tolist() == [0, 5, 6] and model.base_margin == 0.0
+    assert model.nodes['feature'].tolist() == [2, -1, 0, -1, -1, -1]
+    x = np.array([[0, 0, 0.25], [0, 0, 0.5], [3, 0, 0.5], [np.nan, 0, 0.75], [9, 0, np.nan], [np.nan, 0, np.nan]], dtype=np.float32)
+    margins = oracle.gbdt_predict(x, model.nodes, model.tree_offsets, model.base_margin, logistic=False)
+    assert margins.tolist() == [-0.125, 0.625, 1.625, 0.625, 1.625, 0.625]
+    probabilities = oracle.gbdt_predict(x, model.nodes, model.tree_offsets, model.base_margin, logistic=True)
+    assert np.allclose(probabilities, 1.0 / (1.0 + np.exp(-margins.astype(np.float64))), rtol=1e-6)
+
+
+def test_model_match_selection():
+    """predict.py:242-249: maximum of the test_index, above 0.9, attained once."""
+    from doppelspeller_b200 import gbdt
+    test_index = np.array([0, 0, 0, 1, 1, 2, 2, 3])
+    predictions = np.array([0.95, 0.99, 0.2, 0.97, 0.97, 0.5, 0.89, 0.91], dtype=np.float32)
+    assert gbdt.select_model_matches(test_index, predictions).tolist() == [1, 7]   # 1: tie at the maximum, 2: below 0.9
