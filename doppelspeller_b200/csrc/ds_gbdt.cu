@@ -11,24 +11,42 @@
 //             margin = base_margin + psum;  reg:logistic / binary:logistic: 1 / (1 + exp(-margin)) in float32.
 //
 // One thread per row.  The trees of a model (<= 1000 x <= 63 nodes x 16 B = 1 MB) are streamed through shared
-// memory in chunks shared by the 256 rows of a CTA; a row's 264 bytes of features stay L1 resident.
+// memory in chunks shared by the 256 rows of a CTA; the CTA's 256 x 66 features are staged once, feature major
+// with a row stride of 257 floats (conflict-free transposing stores; a lane reads bank (feature + lane) mod 32).
 #include "ds_common.cuh"
 
 namespace ds {
 
 constexpr int GBDT_THREADS = 256;
-constexpr int GBDT_CHUNK_NODES = 2560;   // 40 KB of nodes per chunk (static shared memory)
+constexpr int GBDT_CHUNK_NODES = 2560;   // 40 KB of nodes per chunk
 
 static_assert(sizeof(ds_gbdt_node) == 16, "ds_gbdt_node must be 16 bytes");
 
+template <bool STAGED>
 __global__ void __launch_bounds__(GBDT_THREADS) k_gbdt_predict(const float *__restrict__ features, int64_t n_rows, int n_features,
                                                                const ds_gbdt_node *__restrict__ nodes,
                                                                const int32_t *__restrict__ tree_offsets, int n_trees, float base_margin,
                                                                int transform, float *__restrict__ out) {
-    __shared__ uint4 s_nodes[GBDT_CHUNK_NODES];
+    extern __shared__ __align__(16) unsigned char gbdt_smem[];
+    uint4 *s_nodes = reinterpret_cast<uint4 *>(gbdt_smem);
+    float *s_x = reinterpret_cast<float *>(gbdt_smem + (size_t)GBDT_CHUNK_NODES * 16);
     __shared__ int s_first_tree, s_last_tree;
-    const int64_t row = (int64_t)blockIdx.x * GBDT_THREADS + threadIdx.x;
+    const int64_t row0 = (int64_t)blockIdx.x * GBDT_THREADS;
+    const int64_t row = row0 + threadIdx.x;
+    // x[f * x_stride]: this row's feature f
     const float *x = features + (row < n_rows ? row : 0) * (int64_t)n_features;
+    int x_stride = 1;
+    if (STAGED) {
+        const int64_t rows_here = min((int64_t)GBDT_THREADS, n_rows - row0);
+        const float *src = features + row0 * (int64_t)n_features;
+        for (int64_t e = threadIdx.x; e < rows_here * n_features; e += GBDT_THREADS) {
+            const int r = (int)(e / n_features), f = (int)(e % n_features);
+            s_x[f * (GBDT_THREADS + 1) + r] = src[e];
+        }
+        x = s_x + threadIdx.x;
+        x_stride = GBDT_THREADS + 1;
+        __syncthreads();
+    }
     float psum = 0.0f;
     int tree = 0;
     while (tree < n_trees) {
@@ -47,7 +65,7 @@ __global__ void __launch_bounds__(GBDT_THREADS) k_gbdt_predict(const float *__re
             int node = 0;
             ds_gbdt_node nd = t[0];
             while (nd.feature >= 0) {
-                const float v = x[nd.feature];
+                const float v = x[nd.feature * x_stride];
                 node = isnan(v) ? nd.missing : (v < nd.value ? nd.yes : nd.no);
                 nd = t[node];
             }
@@ -61,15 +79,35 @@ __global__ void __launch_bounds__(GBDT_THREADS) k_gbdt_predict(const float *__re
         for (int i = threadIdx.x; i < node1 - node0; i += GBDT_THREADS) s_nodes[i] = src[i];
         __syncthreads();
         if (row < n_rows) {
-            for (int t = first; t < last; ++t) {
+            // one step down a tree; a leaf stays where it is
+            auto step = [&](uint4 raw, int root) -> uint4 {
+                if ((int)raw.x < 0) return raw;
+                const float v = x[raw.x * x_stride];
+                const int yes = raw.z & 0xffff, no = raw.z >> 16, missing = raw.w & 0xffff;
+                const int next = isnan(v) ? missing : (v < __uint_as_float(raw.y) ? yes : no);
+                return s_nodes[root + next];
+            };
+            int t = first;
+            // four trees are walked at once (independent dependency chains); their leaves are added in tree order
+            for (; t + 4 <= last; t += 4) {
+                const int root0 = tree_offsets[t] - node0, root1 = tree_offsets[t + 1] - node0;
+                const int root2 = tree_offsets[t + 2] - node0, root3 = tree_offsets[t + 3] - node0;
+                uint4 r0 = s_nodes[root0], r1 = s_nodes[root1], r2 = s_nodes[root2], r3 = s_nodes[root3];
+                while ((int)(r0.x & r1.x & r2.x & r3.x) >= 0) {   // some walk has not reached its leaf (feature -1) yet
+                    r0 = step(r0, root0);
+                    r1 = step(r1, root1);
+                    r2 = step(r2, root2);
+                    r3 = step(r3, root3);
+                }
+                psum = __fadd_rn(psum, __uint_as_float(r0.y));
+                psum = __fadd_rn(psum, __uint_as_float(r1.y));
+                psum = __fadd_rn(psum, __uint_as_float(r2.y));
+                psum = __fadd_rn(psum, __uint_as_float(r3.y));
+            }
+            for (; t < last; ++t) {
                 const int root = tree_offsets[t] - node0;
                 uint4 raw = s_nodes[root];
-                while ((int)raw.x >= 0) {
-                    const float v = x[raw.x];
-                    const int yes = raw.z & 0xffff, no = raw.z >> 16, missing = raw.w & 0xffff;
-                    const int next = isnan(v) ? missing : (v < __uint_as_float(raw.y) ? yes : no);
-                    raw = s_nodes[root + next];
-                }
+                while ((int)raw.x >= 0) raw = step(raw, root);
                 psum = __fadd_rn(psum, __uint_as_float(raw.y));
             }
         }
@@ -147,8 +185,17 @@ int ds_gbdt_predict(const float *features, int64_t n_rows, int32_t n_features, c
         DS_CUDA(cudaMemcpyAsync(d_zero, &zero, 4, cudaMemcpyHostToDevice, stream));
         d_offsets = d_zero;
     }
-    k_gbdt_predict<<<(unsigned)ceil_div(n_rows, GBDT_THREADS), GBDT_THREADS, 0, stream>>>(d_features, n_rows, n_features, d_nodes, d_offsets,
-                                                                                       n_trees, base_margin, transform, d_out);
+    const size_t node_bytes = (size_t)GBDT_CHUNK_NODES * 16;
+    const size_t staged_bytes = node_bytes + (size_t)n_features * (GBDT_THREADS + 1) * 4;
+    const unsigned blocks = (unsigned)ceil_div(n_rows, GBDT_THREADS);
+    if (staged_bytes <= 112 * 1024) {   // two CTAs per SM
+        DS_CHECK(ensure_dynamic_smem(reinterpret_cast<const void *>(&k_gbdt_predict<true>), staged_bytes));
+        k_gbdt_predict<true><<<blocks, GBDT_THREADS, staged_bytes, stream>>>(d_features, n_rows, n_features, d_nodes, d_offsets, n_trees,
+                                                                            base_margin, transform, d_out);
+    } else {
+        k_gbdt_predict<false><<<blocks, GBDT_THREADS, node_bytes, stream>>>(d_features, n_rows, n_features, d_nodes, d_offsets, n_trees,
+                                                                           base_margin, transform, d_out);
+    }
     DS_LAUNCHED("k_gbdt_predict");
     return ws.finish_outputs();
 }
