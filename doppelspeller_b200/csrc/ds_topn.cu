@@ -820,38 +820,57 @@ __global__ void __launch_bounds__(128) k_select(SelectParams p) {
         return;
     }
     const int n_old = p.ret_n[b];
-    for (int i = lane; i < n_old; i += 32) {
-        s_score[n + i] = p.ret_score[(size_t)b * p.m + i];
-        s_row[n + i] = p.ret_row[(size_t)b * p.m + i];
+    // Candidates [0, n) are padded to a power of two with entries that lose every comparison and sorted in place
+    // (bitonic, best first in this mode's order); the old list, already sorted, sits behind them.
+    int padded = 1;
+    while (padded < n) padded <<= 1;
+    for (int i = n + lane; i < padded; i += 32) {
+        s_score[i] = -INFINITY;
+        s_row[i] = -1;
     }
-    const int total = n + n_old;
+    double *o_score = s_score + padded;
+    int32_t *o_row = s_row + padded;
+    for (int i = lane; i < n_old; i += 32) {
+        o_score[i] = p.ret_score[(size_t)b * p.m + i];
+        o_row[i] = p.ret_row[(size_t)b * p.m + i];
+    }
     __syncwarp();
-    // Final rank of every element in the union.  The old list [n, n + n_old) is already sorted in this mode's
-    // order, so: a candidate ranks behind the candidates that beat it plus a binary search into the old list; an
-    // old element keeps its position plus the candidates that beat it.  (n^2 + n * n_old instead of (n + n_old)^2.)
-    const double *o_score = s_score + n;
-    const int32_t *o_row = s_row + n;
-    for (int i = lane; i < total; i += 32) {
-        const double si = s_score[i];
-        const int ri = s_row[i];
-        int rank = 0;
-        if (by_row) {
-            for (int j = 0; j < n; ++j) rank += s_row[j] > ri;
-        } else {
-            for (int j = 0; j < n; ++j) rank += better(s_score[j], s_row[j], si, ri);
-        }
-        if (i < n) {
-            int lo = 0, hi = n_old;
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                const bool ahead = by_row ? (o_row[mid] > ri) : better(o_score[mid], o_row[mid], si, ri);
-                if (ahead) lo = mid + 1;
-                else hi = mid;
+    for (int span = 2; span <= padded; span <<= 1) {
+        for (int j = span >> 1; j > 0; j >>= 1) {
+            for (int t = lane; t < (padded >> 1); t += 32) {
+                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // bit j clear
+                const int hi = lo | j;
+                const double s_lo = s_score[lo], s_hi = s_score[hi];
+                const int r_lo = s_row[lo], r_hi = s_row[hi];
+                const bool hi_ahead = by_row ? (r_hi > r_lo) : better(s_hi, r_hi, s_lo, r_lo);
+                const bool best_first = (lo & span) == 0;
+                if (hi_ahead == best_first) {
+                    s_score[lo] = s_hi;
+                    s_row[lo] = r_hi;
+                    s_score[hi] = s_lo;
+                    s_row[hi] = r_lo;
+                }
             }
-            rank += lo;
-        } else {
-            rank += i - n;
+            __syncwarp();
         }
+    }
+    // Final rank in the union of two sorted lists: own position plus a binary search into the other list.
+    const int total = n + n_old;
+    for (int i = lane; i < total; i += 32) {
+        const bool is_new = i < n;
+        const int own = is_new ? i : i - n;
+        const double si = is_new ? s_score[own] : o_score[own];
+        const int ri = is_new ? s_row[own] : o_row[own];
+        const double *other_score = is_new ? o_score : s_score;
+        const int32_t *other_row = is_new ? o_row : s_row;
+        int lo = 0, hi = is_new ? n_old : n;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const bool ahead = by_row ? (other_row[mid] > ri) : better(other_score[mid], other_row[mid], si, ri);
+            if (ahead) lo = mid + 1;
+            else hi = mid;
+        }
+        const int rank = own + lo;
         if (rank < p.m) {
             p.ret_score[(size_t)b * p.m + rank] = si;
             p.ret_row[(size_t)b * p.m + rank] = ri;
@@ -1214,7 +1233,9 @@ static int launch_post(const Index &ix, cudaStream_t stream, PostParams pp, int 
 
 static int launch_select(cudaStream_t stream, SelectParams sp) {
     if (sp.n_batch <= 0) return DS_OK;
-    int items = std::max(sp.cap, sp.dense_rows) + sp.m;
+    int widest = 1;   // candidates are padded to a power of two for the in-place sort
+    while (widest < std::max(sp.cap, sp.dense_rows)) widest <<= 1;
+    int items = widest + sp.m;
     sp.max_items = items;
     size_t smem = (size_t)4 * items * 12;
     DS_CHECK(ensure_dynamic_smem(reinterpret_cast<const void *>(&k_select), smem));
