@@ -54,6 +54,7 @@ static_assert(sizeof(chunk_t) == CHUNK_COLS * 2, "chunk type and CHUNK_COLS disa
 __device__ __forceinline__ chunk_t zero_chunk() { return make_uint2(0, 0); }
 constexpr int MAX_SLOTS = 2048;     // slot 0 = "column not in this tile"
 constexpr int CAND_CAP_MAX = 1024;  // per query candidate buffer (per scan launch): clamp(8 * k, 256, 1024)
+constexpr int CAND_CAP_WIDE = 4096; // second try for the queries whose buffer overflowed (massive ties), before the dense fallback
 constexpr int DENSE_ROWS = 256;     // rows of the first (dense, threshold seeding) chunk
 constexpr int FIXED_ROWS = 1024;    // chunk rows of the bounded-memory fallback / rescan passes
 constexpr int QUERY_BATCH = 65536;  // queries per workspace batch
@@ -1258,7 +1259,7 @@ struct PipelineOut {
 };
 
 static int run_pipeline(Workspace &call_ws, const Index &ix, const QuerySet &qs, const std::vector<int32_t> &batch, int mode,
-                        int k, int m, bool fixed, const double *d_threshold, const PipelineOut &out,
+                        int k, int m, bool fixed, bool wide, const double *d_threshold, const PipelineOut &out,
                         std::vector<int32_t> *overflowed) {
     cudaStream_t stream = call_ws.stream();
     const int n_batch = (int)batch.size();
@@ -1274,7 +1275,7 @@ static int run_pipeline(Workspace &call_ws, const Index &ix, const QuerySet &qs,
     uint2 *d_cand = nullptr;
     double *d_ret_score = nullptr, *d_theta = nullptr;
     float *d_dense = nullptr;
-    const int cand_cap = mode == MODE_ROW ? CAND_CAP_MAX : std::min(CAND_CAP_MAX, std::max(256, 8 * k));
+    const int cand_cap = wide ? CAND_CAP_WIDE : (mode == MODE_ROW ? CAND_CAP_MAX : std::min(CAND_CAP_MAX, std::max(256, 8 * k)));
     const bool dense_first = mode == MODE_SCORE;
     const int dense_rows = fixed ? FIXED_ROWS : std::max(DENSE_ROWS, ((2 * k + 255) / 256) * 256);
     DS_CHECK(ws.alloc(&d_batch, n_batch));
@@ -1406,20 +1407,28 @@ static int run_pipeline(Workspace &call_ws, const Index &ix, const QuerySet &qs,
     return DS_OK;
 }
 
-// runs `ids` through the pipeline in workspace-sized batches, then redoes the overflowed ones in the
-// bounded-memory form (adversarial row order, massive ties, thresholds <= 0)
+// runs `ids` through the pipeline in workspace-sized batches, then redoes the overflowed ones with wide buffers and
+// what still overflows in the bounded-memory form (adversarial row order, massive ties, thresholds <= 0)
 static int run_batches(Workspace &ws, const Index &ix, const QuerySet &qs, const std::vector<int32_t> &ids, int mode, int k, int m,
                        const double *d_threshold, const PipelineOut &out) {
-    std::vector<int32_t> overflowed;
+    std::vector<int32_t> overflowed, still_overflowed;
     for (size_t i0 = 0; i0 < ids.size(); i0 += QUERY_BATCH) {
         size_t i1 = std::min(ids.size(), i0 + QUERY_BATCH);
         std::vector<int32_t> batch(ids.begin() + i0, ids.begin() + i1);
-        DS_CHECK(run_pipeline(ws, ix, qs, batch, mode, k, m, false, d_threshold, out, &overflowed));
+        DS_CHECK(run_pipeline(ws, ix, qs, batch, mode, k, m, false, false, d_threshold, out, &overflowed));
     }
+    // second try with 4,096-entry buffers (thousands of rows tied at the threshold, e.g. a title the truth DB repeats)
+    const bool wide_fits = (size_t)4 * (CAND_CAP_WIDE + m) * 12 <= 227 * 1024;   // k_select's shared memory (4 warps per CTA)
+    if (!wide_fits) still_overflowed.swap(overflowed);
     for (size_t i0 = 0; i0 < overflowed.size(); i0 += QUERY_BATCH / 8) {
         size_t i1 = std::min(overflowed.size(), i0 + QUERY_BATCH / 8);
         std::vector<int32_t> batch(overflowed.begin() + i0, overflowed.begin() + i1);
-        DS_CHECK(run_pipeline(ws, ix, qs, batch, mode, k, m, true, d_threshold, out, nullptr));
+        DS_CHECK(run_pipeline(ws, ix, qs, batch, mode, k, m, false, true, d_threshold, out, &still_overflowed));
+    }
+    for (size_t i0 = 0; i0 < still_overflowed.size(); i0 += QUERY_BATCH / 8) {
+        size_t i1 = std::min(still_overflowed.size(), i0 + QUERY_BATCH / 8);
+        std::vector<int32_t> batch(still_overflowed.begin() + i0, still_overflowed.begin() + i1);
+        DS_CHECK(run_pipeline(ws, ix, qs, batch, mode, k, m, true, false, d_threshold, out, nullptr));
     }
     return DS_OK;
 }
