@@ -14,6 +14,7 @@ reproduces both, which is what makes the results bit-identical.
 import logging
 import math
 from collections import Counter
+from itertools import chain
 
 import numpy as np
 
@@ -29,17 +30,18 @@ TOO_FEW_ROWS_MESSAGE = 'top_matches.shape[0] != self.top_n'   # match_maker.py:1
 
 
 def _document_frequencies(n_gram_sets):
-    """common.py:145-147 get_n_grams_counter: document frequency over per-title n-gram sets."""
-    return Counter(x for y in n_gram_sets for x in set(y))
+    """common.py:145-147 get_n_grams_counter: document frequency over per-title n-gram sets.  The same sequence as the
+    reference's `Counter(x for y in n_grams for x in set(y))` (first-seen key order feeds the column numbering), produced
+    by C-level iterators instead of a generator frame per element."""
+    return Counter(chain.from_iterable(map(set, n_gram_sets)))
 
 
 def _rows_to_csr(rows, encoding):
+    """CSR of the rows with every set walked in its own iteration order (match_maker.py:172-174)."""
     ptr = np.zeros(len(rows) + 1, dtype=np.int64)
-    cols = []
-    for i, value in enumerate(rows):
-        cols.extend(encoding[x] for x in value)     # the set's own iteration order (match_maker.py:172-174)
-        ptr[i + 1] = len(cols)
-    return ptr, np.array(cols, dtype=np.uint16)
+    np.cumsum(np.fromiter(map(len, rows), dtype=np.int64, count=len(rows)), out=ptr[1:])
+    cols = np.fromiter(map(encoding.__getitem__, chain.from_iterable(rows)), dtype=np.uint16, count=int(ptr[-1]))
+    return ptr, cols
 
 
 class MatchMaker:
