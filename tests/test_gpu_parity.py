@@ -71,6 +71,27 @@ def test_negative_weight_keeps_the_dense_scan():
     assert np.array_equal(kth, want_kth)
 
 
+def test_repeated_truth_titles_overflow_tiers():
+    """A truth DB that repeats titles thousands of times: every copy ties at the top score, the 256 / 1,024-entry candidate
+    buffers overflow, the 4,096-entry retry takes the 1,500-fold title and the dense fallback the 6,000-fold one."""
+    from doppelspeller_b200 import encode, synthetic
+    from oracle import oracle
+    truth = synthetic.generate_truth_titles(24000, seed=81)
+    rng = np.random.default_rng(82)
+    for title, copies in (('acme holdings ltd', 1500), ('northern lights trading company', 6000)):
+        for r in rng.choice(len(truth), copies, replace=False):
+            truth[r] = title
+    test, _ = synthetic.generate_test_titles(truth, 200, seed=83)
+    test[:4] = ['acme holdings ltd', 'northern lights trading company', 'acme holding ltd', 'northern light trading company']
+    enc = encode.encode_canonical(test, truth)
+    for k in (10, 100):
+        rows, count, kth, _ = _match_maker(enc, k)._index.topn(enc['q_ptr'], enc['q_cols'], k, with_details=True)
+        want_rows, want_count, want_kth = oracle.topn(oracle_index_from_encoded(enc), k)
+        assert np.array_equal(count, want_count)
+        assert np.array_equal(rows, want_rows)
+        assert np.array_equal(kth, want_kth)
+
+
 def test_long_title_index_keeps_the_dense_scan():
     """Blocks of 2,048 long titles hold more than 65,535 postings (the 16-bit segment offsets of the posting form):
     such an index stays on the dense row scan; queries with more than 32 trigrams go through both forms elsewhere."""
