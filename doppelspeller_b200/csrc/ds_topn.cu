@@ -682,7 +682,7 @@ __global__ void __launch_bounds__(POST_WARPS * 32, POST_CTAS) k_post(PostParams 
             // sweep and zero the block, 128 rows (4 per lane) at a time; rows above their group's bar wait in `list`
             // (their accumulators stay) for the full filter
             const int base_pos = s * POST_ROWS;
-#pragma unroll 1
+#pragma unroll 2
             for (int i = 0; i < POST_GROUPS; ++i) {
                 const int idx = i * 32 + lane;
                 const float bar = __shfl_sync(0xffffffffu, my_bar, i);
