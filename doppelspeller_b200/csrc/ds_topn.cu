@@ -62,7 +62,8 @@ constexpr int STATE_OVERFLOW = 1;
 constexpr int SORT_BLOCK = 4096;    // rows are length-sorted inside blocks of this many consecutive rows
 constexpr int POST_ROWS = 2048;     // row positions per posting block = f32 accumulators per warp in k_post (8 KB)
 constexpr int POST_WARPS = 13;      // warps per CTA; two CTAs (26 warps, 213 KB of accumulators) per SM
-constexpr int POST_LIST = 64;       // per warp: rows of the swept block waiting for the full filter
+constexpr int POST_LIST = 32;       // per warp: rows of the swept block waiting for the full filter
+constexpr int POST_DESC = 64;       // per warp: listed pieces (start in `post`, idf32, length) of the block being walked
 // tuning knobs of k_post, overridable at build time (-DDS_POST_...=n) for A/B builds; defaults = measured best on C3
 #ifndef DS_POST_RUN
 #define DS_POST_RUN 8
@@ -244,6 +245,41 @@ __global__ void k_sums_floor(const float *__restrict__ sums_pos, int64_t n_rows,
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) low = fminf(low, __shfl_xor_sync(0xffffffffu, low, d));
     if (lane == 0) out[group] = low;
+}
+
+// Re-orders the postings of every long segment so that 32 consecutive entries fall into 32 different shared-memory
+// banks of k_post's accumulators (bank = row & 31): entries are ranked by (index within their bank, bank).  The rows
+// of a segment are distinct and their additions commute, so the order inside a segment is free.  One warp per segment.
+constexpr int BALANCE_WARPS = 4;
+__global__ void __launch_bounds__(BALANCE_WARPS * 32) k_post_balance(uint16_t *__restrict__ post, const post_off_t *__restrict__ seg_off,
+                                                                     const uint32_t *__restrict__ seg_base, int64_t n_segments, int n_vocab) {
+    __shared__ uint16_t s_rows[BALANCE_WARPS][POST_ROWS];
+    __shared__ uint16_t s_rank[BALANCE_WARPS][POST_ROWS];
+    __shared__ int s_count[BALANCE_WARPS][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t seg = (int64_t)blockIdx.x * BALANCE_WARPS + warp;
+    if (seg >= n_segments) return;
+    const int64_t s = seg / n_vocab;
+    const int c = (int)(seg % n_vocab);
+    const post_off_t *o = seg_off + s * (n_vocab + 1) + c;
+    const int n = (int)(o[1] - o[0]);
+    if (n <= 32 || n > POST_ROWS) return;
+    uint16_t *entries = post + seg_base[s] + o[0];
+    s_count[warp][lane] = 0;
+    for (int i = lane; i < n; i += 32) s_rows[warp][i] = entries[i];
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) s_rank[warp][i] = (uint16_t)atomicAdd(&s_count[warp][s_rows[warp][i] & 31], 1);
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+        const int row = s_rows[warp][i], bank = row & 31, k = s_rank[warp][i];
+        int at = 0;
+#pragma unroll
+        for (int b = 0; b < 32; ++b) {
+            const int cnt = s_count[warp][b];
+            at += min(cnt, k) + ((b < bank && cnt > k) ? 1 : 0);
+        }
+        entries[at] = (uint16_t)row;
+    }
 }
 
 // 32-bit segment starts -> per block base + 16-bit offsets (half the table k_post has to keep in L2)
@@ -542,6 +578,8 @@ __global__ void __launch_bounds__(POST_WARPS * 32, POST_CTAS) k_post(PostParams 
     float *acc = reinterpret_cast<float *>(smem) + (size_t)warp * POST_ROWS;
     float4 *acc4 = reinterpret_cast<float4 *>(acc);
     uint16_t *list = reinterpret_cast<uint16_t *>(smem + (size_t)POST_WARPS * POST_ROWS * 4) + warp * POST_LIST;
+    uint2 *desc = reinterpret_cast<uint2 *>(smem + (size_t)POST_WARPS * (POST_ROWS * 4 + POST_LIST * 2)) + warp * POST_DESC;
+    uint8_t *desc_n = smem + (size_t)POST_WARPS * (POST_ROWS * 4 + POST_LIST * 2 + POST_DESC * 8) + warp * POST_DESC;
     if (threadIdx.x == 0) s_next = 0;
     __syncthreads();
     const long long cta_first = (long long)blockIdx.x * p.tasks_per_cta;
@@ -617,65 +655,77 @@ __global__ void __launch_bounds__(POST_WARPS * 32, POST_CTAS) k_post(PostParams 
                         my_w = __ldg(p.w32 + c);
                     }
                 }
-                unsigned pending = __ballot_sync(0xffffffffu, my_end > my_beg);   // non-empty segments, ascending column id
-                uint32_t cur = 0, end = 0;   // warp-uniform cursor into the current segment
-                float w = 0.0f;
-
-                // one ring step: read the accumulators of the oldest piece, request the piece POST_DEPTH ahead (its
-                // address arithmetic covers the shared-memory latency), then add and store
-                auto fill = [&](PostPiece &piece) {
-                    if (cur >= end) {
-                        if (pending == 0) {
-                            piece.n = 0;
-                            return;
-                        }
-                        const int j = __ffs(pending) - 1;
-                        pending &= pending - 1;
-                        cur = base + __shfl_sync(0xffffffffu, my_beg, j);
-                        end = base + __shfl_sync(0xffffffffu, my_end, j);
-                        w = __shfl_sync(0xffffffffu, my_w, j);
-                    }
-                    const int n = (int)min(end - cur, 64u);
-                    piece.n = n;
-                    piece.w = w;
-                    const uint16_t *src = p.post + cur + lane;
-                    if (lane < n) piece.r0 = __ldg(src);
-                    if (n > 32) {
-                        if (lane + 32 < n) piece.r1 = __ldg(src + 32);
-                    }
-                    cur += 64;
-                };
-                PostPiece ring[POST_DEPTH];
+                // The non-empty segments are cut into pieces of <= 64 postings, listed in shared memory in ascending
+                // column order (lane = column: a prefix sum of the piece counts gives every lane its slots); the walk
+                // then is a plain counted loop over the list.  Lists longer than POST_DESC pieces go in rounds.
+                const uint32_t n_mine = my_end > my_beg ? my_end - my_beg : 0u;
+                unsigned remaining = __ballot_sync(0xffffffffu, n_mine != 0);
+                my_beg += base;
+                const uint16_t *lane_post = p.post + lane;
+                while (remaining != 0) {
+                    const bool mine = (remaining >> lane) & 1u;
+                    const uint32_t pieces = mine ? (n_mine + 63u) >> 6 : 0u;
+                    uint32_t incl = pieces;
 #pragma unroll
-                for (int d = 0; d < POST_DEPTH; ++d) {
-                    ring[d].r0 = 0;
-                    ring[d].r1 = 0;
-                    fill(ring[d]);
-                }
-                bool running = true;
-                while (running) {
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += v;
+                    }
+                    const bool fits = mine && incl <= (uint32_t)POST_DESC;
+                    const unsigned fit_mask = __ballot_sync(0xffffffffu, fits);   // a prefix of `remaining`: at least its first lane
+                    const int n_pieces = (int)__shfl_sync(0xffffffffu, incl, 31 - __clz(fit_mask));
+                    if (fits) {
+                        uint32_t at = incl - pieces, start = my_beg, left = n_mine;
+                        for (uint32_t t = 0; t < pieces; ++t) {
+                            desc[at] = make_uint2(start, __float_as_uint(my_w));
+                            desc_n[at] = (uint8_t)min(left, 64u);
+                            ++at;
+                            start += 64u;
+                            left -= 64u;
+                        }
+                    }
+                    remaining &= ~fit_mask;
+                    __syncwarp();
+
+                    // ring of POST_DEPTH pieces in flight: read the accumulators of the oldest piece, request the piece
+                    // POST_DEPTH ahead (its address arithmetic covers the shared-memory latency), then add and store
+                    auto fetch = [&](int index, PostPiece &piece) {
+                        const uint2 d = desc[index];
+                        const int n = desc_n[index];
+                        piece.n = n;
+                        piece.w = __uint_as_float(d.y);
+                        const uint16_t *src = lane_post + d.x;
+                        if (lane < n) piece.r0 = __ldg(src);
+                        if (lane + 32 < n) piece.r1 = __ldg(src + 32);
+                    };
+                    PostPiece ring[POST_DEPTH];
 #pragma unroll
                     for (int d = 0; d < POST_DEPTH; ++d) {
-                        const int n = ring[d].n;
-                        if (n == 0) {
-                            running = false;
-                            break;
-                        }
-                        const float add = ring[d].w;
-                        float *slot0 = acc + ring[d].r0, *slot1 = acc + ring[d].r1;
-                        const bool first = lane < n, second = lane + 32 < n;
-                        float a0 = 0.0f, a1 = 0.0f;
-                        if (first) a0 = *slot0;
-                        if (n > 32) {
-                            if (second) a1 = *slot1;
-                        }
-                        fill(ring[d]);
-                        if (first) *slot0 = __fadd_rn(a0, add);
-                        if (n > 32) {
-                            if (second) *slot1 = __fadd_rn(a1, add);
-                        }
-                        __syncwarp();   // the next piece may belong to the next column and touch the same rows
+                        ring[d].r0 = 0;
+                        ring[d].r1 = 0;
+                        ring[d].n = 0;
+                        ring[d].w = 0.0f;
+                        if (d < n_pieces) fetch(d, ring[d]);
                     }
+                    for (int first_piece = 0; first_piece < n_pieces; first_piece += POST_DEPTH) {
+#pragma unroll
+                        for (int d = 0; d < POST_DEPTH; ++d) {
+                            const int index = first_piece + d;
+                            if (index >= n_pieces) break;
+                            const int n = ring[d].n;
+                            const float add = ring[d].w;
+                            float *slot0 = acc + ring[d].r0, *slot1 = acc + ring[d].r1;
+                            const bool first = lane < n, second = lane + 32 < n;
+                            float a0 = 0.0f, a1 = 0.0f;
+                            if (first) a0 = *slot0;
+                            if (second) a1 = *slot1;
+                            if (index + POST_DEPTH < n_pieces) fetch(index + POST_DEPTH, ring[d]);
+                            if (first) *slot0 = __fadd_rn(a0, add);
+                            if (second) *slot1 = __fadd_rn(a1, add);
+                            __syncwarp();   // the next piece may belong to the next column and touch the same rows
+                        }
+                    }
+                    __syncwarp();   // the list is rewritten by the next round
                 }
             }
 
@@ -1213,7 +1263,7 @@ static int launch_post(const Index &ix, cudaStream_t stream, PostParams pp, int 
     pp.tasks_per_cta = (int)std::min<long long>(POST_WARPS * DS_POST_TASKS, std::max<long long>(POST_WARPS, ceil_div(pp.n_tasks, (long long)148 * 2 * 2)));
     const long long ctas = ceil_div(pp.n_tasks, (long long)pp.tasks_per_cta);
     if (ctas > INT32_MAX) return fail(DS_ERR_UNSUPPORTED, "too many posting tasks in one launch");
-    const size_t smem = (size_t)POST_WARPS * (POST_ROWS * 4 + POST_LIST * 2);
+    const size_t smem = (size_t)POST_WARPS * (POST_ROWS * 4 + POST_LIST * 2 + POST_DESC * 9);
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     if (g_profile.enabled) {
         DS_CUDA(cudaEventCreate(&ev_start));
@@ -1688,6 +1738,9 @@ int ds_index_create(ds_index **out, int device, int64_t n_truth, int32_t n_vocab
             k_post_build<1><<<(unsigned)ceil_div(n_truth, 256), 256, 0, stream>>>(packed, ix.chunk_ptr, n_truth, n_vocab, d_seg_start, ix.post,
                                                                                   d_post_flags + 1);   // d_seg_start = running cursors from here on
             DS_LAUNCHED("k_post_build");
+            k_post_balance<<<(unsigned)ceil_div(n_seg, BALANCE_WARPS), BALANCE_WARPS * 32, 0, stream>>>(ix.post, ix.seg_off, ix.seg_base, n_seg,
+                                                                                                 n_vocab);
+            DS_LAUNCHED("k_post_balance");
         }
         int h_post_flags[3] = {0, 0, 0};
         DS_CUDA(cudaMemcpyAsync(h_post_flags, d_post_flags, 12, cudaMemcpyDeviceToHost, stream));
