@@ -63,7 +63,7 @@ constexpr int SORT_BLOCK = 4096;    // rows are length-sorted inside blocks of t
 constexpr int POST_ROWS = 2048;     // row positions per posting block = f32 accumulators per warp in k_post (8 KB)
 constexpr int POST_WARPS = 13;      // warps per CTA; two CTAs (26 warps, 213 KB of accumulators) per SM
 constexpr int POST_LIST = 32;       // per warp: rows of the swept block waiting for the full filter
-constexpr int POST_DESC = 64;       // per warp: listed pieces (start in `post`, idf32, length) of the block being walked
+constexpr int POST_DESC = 64;       // per warp: listed pieces (start inside the block's postings | length << 24, idf32) of the block being walked
 // tuning knobs of k_post, overridable at build time (-DDS_POST_...=n) for A/B builds; defaults = measured best on C3
 #ifndef DS_POST_RUN
 #define DS_POST_RUN 8
@@ -579,7 +579,6 @@ __global__ void __launch_bounds__(POST_WARPS * 32, POST_CTAS) k_post(PostParams 
     float4 *acc4 = reinterpret_cast<float4 *>(acc);
     uint16_t *list = reinterpret_cast<uint16_t *>(smem + (size_t)POST_WARPS * POST_ROWS * 4) + warp * POST_LIST;
     uint2 *desc = reinterpret_cast<uint2 *>(smem + (size_t)POST_WARPS * (POST_ROWS * 4 + POST_LIST * 2)) + warp * POST_DESC;
-    uint8_t *desc_n = smem + (size_t)POST_WARPS * (POST_ROWS * 4 + POST_LIST * 2 + POST_DESC * 8) + warp * POST_DESC;
     if (threadIdx.x == 0) s_next = 0;
     __syncthreads();
     const long long cta_first = (long long)blockIdx.x * p.tasks_per_cta;
@@ -660,8 +659,7 @@ __global__ void __launch_bounds__(POST_WARPS * 32, POST_CTAS) k_post(PostParams 
                 // then is a plain counted loop over the list.  Lists longer than POST_DESC pieces go in rounds.
                 const uint32_t n_mine = my_end > my_beg ? my_end - my_beg : 0u;
                 unsigned remaining = __ballot_sync(0xffffffffu, n_mine != 0);
-                my_beg += base;
-                const uint16_t *lane_post = p.post + lane;
+                const uint16_t *lane_post = p.post + base + lane;   // piece starts are kept relative to the block
                 while (remaining != 0) {
                     const bool mine = (remaining >> lane) & 1u;
                     const uint32_t pieces = mine ? (n_mine + 63u) >> 6 : 0u;
@@ -677,8 +675,7 @@ __global__ void __launch_bounds__(POST_WARPS * 32, POST_CTAS) k_post(PostParams 
                     if (fits) {
                         uint32_t at = incl - pieces, start = my_beg, left = n_mine;
                         for (uint32_t t = 0; t < pieces; ++t) {
-                            desc[at] = make_uint2(start, __float_as_uint(my_w));
-                            desc_n[at] = (uint8_t)min(left, 64u);
+                            desc[at] = make_uint2(start | (min(left, 64u) << 24), __float_as_uint(my_w));   // start < 2^24: a block's postings
                             ++at;
                             start += 64u;
                             left -= 64u;
@@ -691,10 +688,10 @@ __global__ void __launch_bounds__(POST_WARPS * 32, POST_CTAS) k_post(PostParams 
                     // POST_DEPTH ahead (its address arithmetic covers the shared-memory latency), then add and store
                     auto fetch = [&](int index, PostPiece &piece) {
                         const uint2 d = desc[index];
-                        const int n = desc_n[index];
+                        const int n = (int)(d.x >> 24);
                         piece.n = n;
                         piece.w = __uint_as_float(d.y);
-                        const uint16_t *src = lane_post + d.x;
+                        const uint16_t *src = lane_post + (d.x & 0xffffffu);
                         if (lane < n) piece.r0 = __ldg(src);
                         if (lane + 32 < n) piece.r1 = __ldg(src + 32);
                     };
@@ -1263,7 +1260,7 @@ static int launch_post(const Index &ix, cudaStream_t stream, PostParams pp, int 
     pp.tasks_per_cta = (int)std::min<long long>(POST_WARPS * DS_POST_TASKS, std::max<long long>(POST_WARPS, ceil_div(pp.n_tasks, (long long)148 * 2 * 2)));
     const long long ctas = ceil_div(pp.n_tasks, (long long)pp.tasks_per_cta);
     if (ctas > INT32_MAX) return fail(DS_ERR_UNSUPPORTED, "too many posting tasks in one launch");
-    const size_t smem = (size_t)POST_WARPS * (POST_ROWS * 4 + POST_LIST * 2 + POST_DESC * 9);
+    const size_t smem = (size_t)POST_WARPS * (POST_ROWS * 4 + POST_LIST * 2 + POST_DESC * 8);
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     if (g_profile.enabled) {
         DS_CUDA(cudaEventCreate(&ev_start));
