@@ -410,6 +410,21 @@ def test_randomised_shapes_against_oracle():
         _check_against_oracle(_tiny_case(truth, queries, n_vocab), k)
 
 
+def test_reference_idf_word_vector_on_the_gpu():
+    """idf_word('first') = log(3 / 2) = 0.40547 (doppelspeller/tests/test_common.py:25-28) as construct_features emits it."""
+    import math
+    from doppelspeller_b200 import feature_engineering as fe
+    from doppelspeller_b200.pipeline import truth_word_counts
+    truth = ['first second first third first', 'first first', 'fifth']
+    counts = truth_word_counts(truth)
+    title = 'first second'
+    la, lb = np.array([len(title)], np.uint8), np.array([len(truth[0])], np.uint8)
+    feats = fe.construct_features(la, lb, fe.encode_title(title)[None], fe.encode_title(truth[0])[None], counts[:1], fe.SPACE_CODE, len(truth))
+    idf = np.asarray(feats)[0, 6 + 2 * 15:6 + 3 * 15]
+    assert round(float(idf[0]), 5) == 0.40547
+    assert np.isclose(idf[0], math.log(3 / 2), rtol=1e-6) and np.isclose(idf[1], math.log(3.0), rtol=1e-6) and np.isnan(idf[5:]).all()
+
+
 # ------------------------------------------------------------------ f3: transform_title
 def test_transform_titles_match_reference(golden_transform):
     """ds_transform_titles (k_transform) against the reference's transform_title outputs: host and device tables."""

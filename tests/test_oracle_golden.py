@@ -96,3 +96,23 @@ def test_transform_title_matches_reference(golden_transform):
     assert [oracle.transform_title(t) for t in titles] == outputs
     assert oracle.transform_title('''LKJblksd skjasl dfkjf &* 8*&&&8 GGdjsdkj--sdsd-"sdi..//' d'  k   bkjh77_asda33''') == \
         'lkjblksd skjasl dfkjf 88 ggdjsdkj sdsd sdi d k bkjh77asda33'
+
+
+def test_reference_word_counter_and_idf_word_vectors():
+    """The reference's own known answers (doppelspeller/tests/test_common.py:21-28): document frequencies over per-title word
+    SETS {'first': 2, 'second': 1, 'third': 1, 'fifth': 1} and idf_word('first') = log(3 / 2) = 0.40547 - here as they reach
+    the hot path: the [n_truth, 15] count table of the pipeline and the idf features (columns 36..50) of construct_features."""
+    import math
+    from doppelspeller_b200 import feature_engineering as fe
+    from doppelspeller_b200.pipeline import truth_word_counts
+    truth = ['first second first third first', 'first first', 'fifth']
+    counts = truth_word_counts(truth)
+    assert counts[0, :5].tolist() == [2, 1, 2, 1, 2] and counts[1, :2].tolist() == [2, 2] and counts[2, 0] == 1
+    assert not counts[0, 5:].any()
+    title = 'first second'
+    la, lb = np.array([len(title)], np.uint8), np.array([len(truth[0])], np.uint8)
+    feats = oracle.construct_features(la, lb, fe.encode_title(title)[None], fe.encode_title(truth[0])[None], counts[:1], fe.SPACE_CODE, len(truth))
+    idf = feats[0, 6 + 2 * 15:6 + 3 * 15]
+    assert round(float(idf[0]), 5) == 0.40547 == round(math.log(3 / 2), 5)           # 'first'
+    assert idf[0] == np.float32(math.log(3 / 2)) and idf[1] == np.float32(math.log(3 / 1))   # 'second'
+    assert np.isnan(idf[5:]).all()
