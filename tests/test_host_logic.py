@@ -107,3 +107,15 @@ def test_model_match_selection():
     test_index = np.array([0, 0, 0, 1, 1, 2, 2, 3])
     predictions = np.array([0.95, 0.99, 0.2, 0.97, 0.97, 0.5, 0.89, 0.91], dtype=np.float32)
     assert gbdt.select_model_matches(test_index, predictions).tolist() == [1, 7]   # 1: tie at the maximum, 2: below 0.9
+
+
+def test_gbdt_dump_feature_names_and_tree_limit():
+    from doppelspeller_b200 import gbdt
+    dump = ['{"nodeid": 0, "split": "ratio", "split_condition": 94.5, "yes": 1, "no": 2, "missing": 1, "children": ['
+            '{"nodeid": 1, "leaf": -1.0}, {"nodeid": 2, "leaf": 2.0}]}', '{"nodeid": 0, "leaf": 7.0}']
+    model = gbdt.GbdtModel.from_xgboost_dump(dump, base_score=0.25, objective='binary:logistic', ntree_limit=1,
+                                             feature_names=['length', 'ratio'])
+    assert model.n_trees == 1 and model.nodes['feature'].tolist() == [1, -1, -1] and model.transform == gbdt.LOGISTIC
+    assert abs(model.base_margin - np.log(0.25 / 0.75)) < 1e-6
+    linear = gbdt.GbdtModel.from_xgboost_dump(dump, base_score=0.5, objective='reg:squarederror')
+    assert linear.transform == gbdt.MARGIN and linear.base_margin == 0.5 and linear.n_trees == 2
