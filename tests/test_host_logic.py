@@ -117,5 +117,5 @@ def test_gbdt_dump_feature_names_and_tree_limit():
                                              feature_names=['length', 'ratio'])
     assert model.n_trees == 1 and model.nodes['feature'].tolist() == [1, -1, -1] and model.transform == gbdt.LOGISTIC
     assert abs(model.base_margin - np.log(0.25 / 0.75)) < 1e-6
-    linear = gbdt.GbdtModel.from_xgboost_dump(dump, base_score=0.5, objective='reg:squarederror')
+    linear = gbdt.GbdtModel.from_xgboost_dump(dump, base_score=0.5, objective='reg:squarederror', feature_names=['length', 'ratio'])
     assert linear.transform == gbdt.MARGIN and linear.base_margin == 0.5 and linear.n_trees == 2
