@@ -24,7 +24,7 @@ MAX_TITLE = 255
 
 # every symbol include/doppelspeller_b200.h declares (tests check that the library exports them all)
 EXPORTED_SYMBOLS = (
-    'ds_version', 'ds_last_error', 'ds_kernel_launches', 'ds_profile_begin', 'ds_profile_end', 'ds_profile_end_split', 'ds_transform_titles',
+    'ds_version', 'ds_last_error', 'ds_kernel_launches', 'ds_trim', 'ds_profile_begin', 'ds_profile_end', 'ds_profile_end_split', 'ds_transform_titles',
     'ds_index_create', 'ds_index_destroy', 'ds_index_get_sums',
     'ds_topn', 'ds_topn_retained', 'ds_topn_local', 'ds_topn_merge', 'ds_topn_rescan',
     'ds_indel_ratio_u8', 'ds_indel_ratio_pairs', 'ds_levenshtein_ratio_pairs',
@@ -51,6 +51,7 @@ _vp, _i64, _i32, _u8, _u32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ct
 lib.ds_version.restype = ctypes.c_int
 lib.ds_last_error.restype = ctypes.c_char_p
 lib.ds_kernel_launches.restype = _i64
+lib.ds_trim.argtypes = [ctypes.c_int]
 lib.ds_topn_retained.restype = _i32
 lib.ds_topn_retained.argtypes = [_i32]
 lib.ds_encode_max_vocab.restype = _i32
@@ -127,6 +128,16 @@ def current_stream():
     if not torch.cuda.is_available():
         return None
     return torch.cuda.current_stream().cuda_stream
+
+
+def stream_for(*arrays):
+    """cudaStream_t the call must be ordered on: torch's current stream OF THE DEVICE that owns the first CUDA tensor
+    among `arrays` (not of torch's current device - the native entry points run where their buffers live)."""
+    import torch
+    for array in arrays:
+        if hasattr(array, 'is_cuda') and array.is_cuda:
+            return torch.cuda.current_stream(array.device).cuda_stream
+    return current_stream()
 
 
 def current_device():

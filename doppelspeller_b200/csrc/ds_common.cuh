@@ -8,7 +8,9 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <initializer_list>
 #include <map>
 #include <mutex>
 #include <utility>
@@ -61,6 +63,26 @@ inline bool is_device_pointer(const void *p) {
         return false;
     }
     return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+// device that owns a device pointer, -1 for host / unknown pointers
+inline int pointer_device(const void *p) {
+    if (p == nullptr) return -1;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) ? attr.device : -1;
+}
+
+// first device found among `pointers`: the device the call must run on (-1: all host buffers -> current device)
+inline int owning_device(std::initializer_list<const void *> pointers) {
+    for (const void *p : pointers) {
+        const int d = pointer_device(p);
+        if (d >= 0) return d;
+    }
+    return -1;
 }
 
 // Stream-ordered device allocation released in the destructor (cudaFreeAsync on the same stream).
@@ -131,7 +153,8 @@ class Workspace {
 
    private:
     // By default the stream-ordered pool hands freed memory back to the OS at every synchronisation, which
-    // would make each call re-map its whole workspace; keep it cached in the pool instead.
+    // would make each call re-map its whole workspace; keep it cached in the pool instead.  The cached bytes are
+    // bounded by DS_POOL_RELEASE_THRESHOLD_MB (environment, default: unbounded) and ds_trim() hands them back.
     static void keep_pool_memory() {
         static thread_local int done_for_device = -1;
         int device = 0;
@@ -139,6 +162,7 @@ class Workspace {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
             uint64_t threshold = UINT64_MAX;
+            if (const char *mb = getenv("DS_POOL_RELEASE_THRESHOLD_MB")) threshold = (uint64_t)strtoull(mb, nullptr, 10) << 20;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
         }
         done_for_device = device;

@@ -759,6 +759,7 @@ int ds_indel_ratio_u8(const uint8_t *a, const uint8_t *b, int64_t stride, const 
     if (n == 0) return DS_OK;
     if (!a || !b || !la || !lb || !out_ratio) return fail(DS_ERR_BAD_ARG, "NULL argument");
     DS_CHECK(require_device());
+    DeviceGuard guard(owning_device({a, b, la, lb, out_ratio, out_dist}));
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     Workspace ws(stream);
     PairSource src;
@@ -778,6 +779,7 @@ int ds_indel_ratio_pairs(const uint8_t *bytes_a, const int64_t *offsets_a, int64
     if (n == 0) return DS_OK;
     if (!bytes_a || !offsets_a || !bytes_b || !offsets_b || !idx_a || !idx_b || !out_ratio) return fail(DS_ERR_BAD_ARG, "NULL argument");
     DS_CHECK(require_device());
+    DeviceGuard guard(owning_device({bytes_a, bytes_b, offsets_a, offsets_b, idx_a, idx_b, out_ratio, out_dist}));
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     Workspace ws(stream);
     PairSource src;
@@ -797,6 +799,7 @@ int ds_levenshtein_ratio_pairs(const uint8_t *bytes_a, const int64_t *offsets_a,
     if (n == 0) return DS_OK;
     if (!bytes_a || !offsets_a || !bytes_b || !offsets_b || !idx_a || !idx_b || !out_ratio) return fail(DS_ERR_BAD_ARG, "NULL argument");
     DS_CHECK(require_device());
+    DeviceGuard guard(owning_device({bytes_a, bytes_b, offsets_a, offsets_b, idx_a, idx_b, out_ratio}));
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     Workspace ws(stream);
     PairSource src;
@@ -815,6 +818,7 @@ int ds_construct_features(const uint8_t *la, const uint8_t *lb, const uint8_t *a
     if (n_pairs == 0) return DS_OK;
     if (!la || !lb || !a || !b || !counts || !out) return fail(DS_ERR_BAD_ARG, "NULL argument");
     DS_CHECK(require_device());
+    DeviceGuard guard(owning_device({a, b, la, lb, counts, out}));
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     Workspace ws(stream);
     PairSource src;
@@ -837,6 +841,7 @@ int ds_construct_features_pairs(const uint8_t *bytes_a, const int64_t *offsets_a
     if (!bytes_a || !offsets_a || !bytes_b || !offsets_b || !counts_b || !idx_a || !idx_b || !out)
         return fail(DS_ERR_BAD_ARG, "NULL argument");
     DS_CHECK(require_device());
+    DeviceGuard guard(owning_device({bytes_a, bytes_b, offsets_a, offsets_b, counts_b, idx_a, idx_b, out}));
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     Workspace ws(stream);
     PairSource src;

@@ -45,6 +45,7 @@ struct ScanProfile {
     double pairs[2] = {0.0, 0.0};
 };
 static ScanProfile g_profile;
+static std::mutex g_profile_lock;   // ds_profile_* and the launch helpers may run on different host threads
 
 constexpr int TQ = 32;              // queries per tile (one bit each in the slot mask)
 constexpr int CHUNK_COLS = 4;       // u16 column ids per chunk: 4 -> one LDG.64 per chunk (7.7 % sentinel padding at the
@@ -85,6 +86,7 @@ constexpr int MODE_ROW = 1;         // retained list = the k highest rows with s
 
 struct Index {
     int device = 0;
+    cudaStream_t last_stream = nullptr;   // stream of the latest call that used the index: ds_index_destroy frees on it
     int64_t n_truth = 0;
     int32_t n_vocab = 0;
     int64_t row_offset = 0;
@@ -1231,8 +1233,9 @@ static int launch_scan(const Index &ix, cudaStream_t stream, ScanParams sp, int 
             k_scan<256><<<grid, 256, smem, stream>>>(part);
         }
         DS_LAUNCHED("k_scan");
-        if (g_profile.enabled) {
+        if (ev_start != nullptr) {
             DS_CUDA(cudaEventRecord(ev_stop, stream));
+            std::lock_guard<std::mutex> guard(g_profile_lock);
             g_profile.events[0].emplace_back(ev_start, ev_stop);
             g_profile.pairs[0] += (double)rows * (double)n_queries * ((double)nt / (double)n_tiles);
         }
@@ -1270,8 +1273,9 @@ static int launch_post(const Index &ix, cudaStream_t stream, PostParams pp, int 
     DS_CHECK(ensure_dynamic_smem(reinterpret_cast<const void *>(&k_post), smem));
     k_post<<<(unsigned)ctas, POST_WARPS * 32, smem, stream>>>(pp);
     DS_LAUNCHED("k_post");
-    if (g_profile.enabled) {
+    if (ev_start != nullptr) {
         DS_CUDA(cudaEventRecord(ev_stop, stream));
+        std::lock_guard<std::mutex> guard(g_profile_lock);
         g_profile.events[1].emplace_back(ev_start, ev_stop);
         const int64_t rows = std::min<int64_t>(ix.n_truth, (int64_t)s1 * POST_ROWS) - (int64_t)s0 * POST_ROWS;
         g_profile.pairs[1] += (double)rows * (double)pp.n_batch;
@@ -1547,6 +1551,7 @@ extern "C" {
 int ds_version(void) { return DS_VERSION; }
 
 int ds_profile_begin(void) {
+    std::lock_guard<std::mutex> guard(g_profile_lock);
     for (auto &events : g_profile.events) {
         for (auto &e : events) {
             cudaEventDestroy(e.first);
@@ -1560,6 +1565,7 @@ int ds_profile_begin(void) {
 }
 
 int ds_profile_end_split(double *ms, int64_t *launches, double *pairs) {
+    std::lock_guard<std::mutex> guard(g_profile_lock);
     g_profile.enabled = false;
     for (int kernel = 0; kernel < 2; ++kernel) {
         double total = 0.0;
@@ -1591,6 +1597,18 @@ int ds_profile_end(double *scan_ms, int64_t *scan_launches, double *scan_pairs) 
 }
 const char *ds_last_error(void) { return g_last_error; }
 int64_t ds_kernel_launches(void) { return g_kernel_launches.load(); }
+
+int ds_trim(int device) {
+    int n_devices = 0;
+    if (cudaGetDeviceCount(&n_devices) != cudaSuccess || device < 0 || device >= n_devices) {
+        cudaGetLastError();
+        return fail(DS_ERR_BAD_ARG, "device %d out of range", device);
+    }
+    cudaMemPool_t pool;
+    DS_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    DS_CUDA(cudaMemPoolTrimTo(pool, 0));
+    return DS_OK;
+}
 
 int32_t ds_topn_retained(int32_t k) {
     int extra = std::max(32, k / 4);
@@ -1655,6 +1673,7 @@ int ds_index_create(ds_index **out, int device, int64_t n_truth, int32_t n_vocab
     ix.n_vocab = n_vocab;
     ix.row_offset = global_row_offset;
     ix.n_total = n_truth_total > 0 ? n_truth_total : n_truth;
+    ix.last_stream = stream;
     int status = [&]() -> int {
         Workspace ws(stream);
         const int64_t *d_ptr = nullptr;
@@ -1766,11 +1785,12 @@ int ds_index_destroy(ds_index *index) {
     if (index == nullptr) return DS_OK;
     DeviceGuard guard(index->ix.device);
     // stream-ordered frees (the buffers come from the same pool as the per-call workspace): no device-wide
-    // synchronisation, unlike cudaFree
+    // synchronisation, unlike cudaFree.  Freed on the stream of the latest call that used the index, so the
+    // pool cannot hand the memory out again while kernels of that call are still in flight.
     void *buffers[] = {index->ix.chunks, index->ix.chunk_ptr, index->ix.sums, index->ix.sums_pos, index->ix.perm, index->ix.w32, index->ix.w64,
                        index->ix.post, index->ix.seg_off, index->ix.seg_base, index->ix.sums_floor};
     for (void *b : buffers)
-        if (b != nullptr) cudaFreeAsync(b, nullptr);
+        if (b != nullptr) cudaFreeAsync(b, index->ix.last_stream);
     delete index;
     return DS_OK;
 }
@@ -1779,6 +1799,7 @@ int ds_index_get_sums(const ds_index *index, float *out, void *stream_) {
     if (index == nullptr || out == nullptr) return fail(DS_ERR_BAD_ARG, "index / out is NULL");
     DeviceGuard guard(index->ix.device);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const_cast<ds_index *>(index)->ix.last_stream = stream;
     DS_CUDA(cudaMemcpyAsync(out, index->ix.sums, (size_t)index->ix.n_truth * 4, cudaMemcpyDefault, stream));
     if (!is_device_pointer(out)) DS_CUDA(cudaStreamSynchronize(stream));
     return DS_OK;
@@ -1791,6 +1812,7 @@ int ds_topn_local(ds_index *index, int64_t n_q, const int64_t *q_row_ptr, const 
     const Index &ix = index->ix;
     DeviceGuard guard(ix.device);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    index->ix.last_stream = stream;
     if (n_q == 0) return DS_OK;
     Workspace ws(stream);
     QuerySet qs;
@@ -1854,6 +1876,7 @@ int ds_topn_rescan(ds_index *index, int64_t n_q, const int64_t *q_row_ptr, const
     const Index &ix = index->ix;
     DeviceGuard guard(ix.device);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    index->ix.last_stream = stream;
     if (n_q == 0) return DS_OK;
     Workspace ws(stream);
     const int32_t *d_flags = nullptr;
@@ -1900,6 +1923,7 @@ int ds_topn(ds_index *index, int64_t n_q, const int64_t *q_row_ptr, const uint16
         return fail(DS_ERR_BAD_ARG, "ds_topn needs an unsharded index; use ds_topn_local / _merge / _rescan for shards");
     DeviceGuard guard(ix.device);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    index->ix.last_stream = stream;
     if (n_q == 0) return DS_OK;
     Workspace ws(stream);
     QuerySet qs;

@@ -68,7 +68,7 @@ def construct_features(title_number_of_characters, truth_number_of_characters, t
     target = out if direct else (out.contiguous() if cuda else np.ascontiguousarray(out))
     nat.check(nat.lib.ds_construct_features(
         nat.ptr(la), nat.ptr(lb), nat.ptr(title), nat.ptr(title_truth), stride, nat.ptr(counts), int(space_code),
-        int(number_of_truth_titles), n_pairs, nat.ptr(target), nat.current_stream()))
+        int(number_of_truth_titles), n_pairs, nat.ptr(target), nat.stream_for(title, target)))
     if not direct:
         out[...] = target
     return response
@@ -94,7 +94,7 @@ def fast_levenshtein_ratio_batch(sequences, sequences_to_compare_against, length
         dist = np.empty(n, dtype=np.uint16) if with_distance else None
         a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
     nat.check(nat.lib.ds_indel_ratio_u8(nat.ptr(a), nat.ptr(b), stride, nat.ptr(la), nat.ptr(lb), n, nat.ptr(out),
-                                        nat.ptr(dist), nat.current_stream()))
+                                        nat.ptr(dist), nat.stream_for(a, out)))
     return (out, dist) if with_distance else out
 
 
@@ -169,5 +169,5 @@ def construct_features_pairs(title_table, truth_table, truth_words_counts, title
     nat.check(nat.lib.ds_construct_features_pairs(
         nat.ptr(bytes_a), nat.ptr(off_a), int(off_a.shape[0]) - 1, nat.ptr(bytes_b), nat.ptr(off_b), int(off_b.shape[0]) - 1,
         nat.ptr(truth_words_counts), nat.ptr(title_index), nat.ptr(truth_index), int(space_code),
-        int(number_of_truth_titles), n_pairs, nat.ptr(response), nat.current_stream()))
+        int(number_of_truth_titles), n_pairs, nat.ptr(response), nat.stream_for(title_index, response)))
     return response

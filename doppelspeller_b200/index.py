@@ -136,6 +136,6 @@ def topn_merge(all_score, all_row, k, n_total, q_mx=None, device=0):
     thr = _empty((n_q,), 'float64', cuda, dev)
     flags = _empty((n_q,), 'int32', cuda, dev)
     nat.check(nat.lib.ds_topn_merge(n_shards, n_q, k, n_total, nat.ptr(all_score), nat.ptr(all_row), nat.ptr(q_mx),
-                                    nat.ptr(rows), nat.ptr(count), nat.ptr(kth), nat.ptr(thr), nat.ptr(flags), int(device),
-                                    nat.current_stream()))
+                                    nat.ptr(rows), nat.ptr(count), nat.ptr(kth), nat.ptr(thr), nat.ptr(flags),
+                                    int(dev.index) if cuda else int(device), nat.stream_for(all_score)))
     return rows, count, kth, thr, flags

@@ -148,10 +148,12 @@ class MatchMaker:
         if hasattr(rows, 'cpu'):              # device-resident queries (canonical order): results to the host once
             rows, count, flags = rows.cpu().numpy(), count.cpu().numpy(), flags.cpu().numpy()
         self._rows, self._count, self._flags = rows, count, flags
+        self._rows_top_n = self.top_n
 
     def closest_rows(self):
-        """All queries at once: (truth row indexes int64[Q, top_n] in descending row order, count[Q])."""
-        if self._rows is None:
+        """All queries at once: (truth row indexes int64[Q, top_n] in descending row order, count[Q]).
+        `top_n` is read on every call like the reference does (match_maker.py:187): changing it recomputes."""
+        if self._rows is None or getattr(self, '_rows_top_n', None) != self.top_n:
             self._compute_all()
         return self._rows, self._count
 

@@ -72,7 +72,7 @@ def _ratio_pairs(bytes_a, off_a, n_a, bytes_b, off_b, n_b, idx_a, idx_b):
     out = torch.empty(n, dtype=torch.int32, device=idx_a.device)
     if n:
         nat.check(nat.lib.ds_levenshtein_ratio_pairs(nat.ptr(bytes_a), nat.ptr(off_a), n_a, nat.ptr(bytes_b), nat.ptr(off_b), n_b,
-                                                     nat.ptr(idx_a), nat.ptr(idx_b), n, nat.ptr(out), nat.current_stream()))
+                                                     nat.ptr(idx_a), nat.ptr(idx_b), n, nat.ptr(out), nat.stream_for(idx_a)))
     return out
 
 

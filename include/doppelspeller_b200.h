@@ -56,6 +56,11 @@ int ds_version(void);
 const char *ds_last_error(void);
 /* number of CUDA kernels this library has launched in the calling process (bench.py gpu_launches) */
 int64_t ds_kernel_launches(void);
+/* Hands the stream-ordered allocator's cached (idle) workspace memory of `device` back to the driver.  The library
+ * keeps freed per-call workspaces cached in the device's default memory pool (bounded by the environment variable
+ * DS_POOL_RELEASE_THRESHOLD_MB, default unbounded) so that consecutive calls do not re-map gigabytes; a process that
+ * shares the GPU with another allocator (torch's caching allocator uses cudaMalloc) calls this between phases. */
+int ds_trim(int device);
 /* Measurement hooks (bench.py roofline): between ds_profile_begin and ds_profile_end every launch of the
  * K1 scan kernels (k_scan, k_post) is bracketed by CUDA events on its own stream.  ds_profile_end waits
  * for them and returns the summed device time, the launch count and the (query, truth) pairs scanned. */

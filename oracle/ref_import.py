@@ -1,9 +1,12 @@
-"""Container-only loader for the UNMODIFIED reference (test infrastructure, never shipped).
+"""Loader for the UNMODIFIED reference (test infrastructure, never shipped).
 
-Imports `/root/reference/doppelspeller` read-only so the oracle restatement (`oracle/ds_oracle.c`,
-`oracle/oracle.py`) can be pinned against the reference's own numba kernels and so
-`tests/golden/make_golden.py` can mint golden vectors.  `/root/reference` does not exist on the GPU
-box: nothing under `tests/ -m gpu`, `bench.py` or `__graft_entry__.smoke()` may import this module.
+Imports the reference's `doppelspeller` package from `oracle/_ref` (staged by `oracle/stage_reference.py`, an
+offline `pip install --target` of /root/reference; git-ignored, travels to the GPU box) so that the oracle
+restatement (`oracle/ds_oracle.c`, `oracle/oracle.py`) can be pinned against the reference's own numba kernels,
+`tests/golden/make_golden.py` can mint golden vectors, `oracle/dropin.py` can run the reference's `Prediction`
+with and without the three swapped imports of INTEGRATION.md, and `bench.py --impl reference` can time the
+reference's own kernels.  `/root/reference` itself does not exist on the GPU box and is never read at run time
+there: only the staged copy is.
 
 Shims needed:
   * `Levenshtein` (python-levenshtein==0.12.0, requirements.txt:9) is not installed and
@@ -12,7 +15,6 @@ Shims needed:
   * `xgboost` (predict.py:6, train.py) is not installed -> empty stub module.
   * `PROJECT_DATA_PATH` (settings.py:8-12) -> a temp dir with the gunzipped example CSVs.
 """
-import gzip
 import os
 import shutil
 import sys
@@ -20,10 +22,26 @@ import tempfile
 import types
 
 REFERENCE_ROOT = '/root/reference'
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')
+
+
+def _staged():
+    return os.path.isfile(os.path.join(STAGED_ROOT, 'doppelspeller', 'match_maker.py')) and \
+        os.path.isfile(os.path.join(STAGED_ROOT, 'example_dataset', 'example_truth.csv'))
 
 
 def reference_available():
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, 'doppelspeller'))
+    """True when the staged copy exists, or can be made (the build container holds /root/reference)."""
+    if _staged():
+        return True
+    if os.path.isdir(os.path.join(REFERENCE_ROOT, 'doppelspeller')):
+        try:
+            from oracle import stage_reference
+            stage_reference.stage()
+        except Exception:
+            return False
+        return _staged()
+    return False
 
 
 def _indel_ratio_py(a, b):
@@ -49,17 +67,16 @@ _DATA_DIR = None
 
 
 def stage_example_data():
-    """Gunzip example_dataset/*.csv.gz into a temp dir and return it (settings.py:18,22,36-37)."""
+    """A private copy of the staged example CSVs (settings.py:18,22,36-37; the reference writes its outputs beside
+    them) - returns the directory `PROJECT_DATA_PATH` must point at."""
     global _DATA_DIR
     if _DATA_DIR is not None:
         return _DATA_DIR
     target = tempfile.mkdtemp(prefix='ds_ref_data_')
-    source = os.path.join(REFERENCE_ROOT, 'example_dataset')
+    source = os.path.join(STAGED_ROOT, 'example_dataset')
     for name in os.listdir(source):
-        if name.endswith('.csv.gz'):
-            with gzip.open(os.path.join(source, name), 'rb') as fin, \
-                    open(os.path.join(target, name[:-3]), 'wb') as fout:
-                shutil.copyfileobj(fin, fout)
+        if name.endswith('.csv'):
+            shutil.copyfile(os.path.join(source, name), os.path.join(target, name))
     _DATA_DIR = target
     return target
 
@@ -68,7 +85,7 @@ def import_reference():
     """Returns the imported reference modules as a namespace (common, match_maker, feature_engineering,
     predict, settings, constants)."""
     if not reference_available():
-        raise RuntimeError('/root/reference is not present (GPU box?) - the reference cannot be imported here')
+        raise RuntimeError('the reference is not staged under oracle/_ref (run oracle/stage_reference.py in the build container)')
     if 'Levenshtein' not in sys.modules:
         lev = types.ModuleType('Levenshtein')
         lev.ratio = _indel_ratio_py
@@ -76,8 +93,8 @@ def import_reference():
     if 'xgboost' not in sys.modules:
         sys.modules['xgboost'] = types.ModuleType('xgboost')
     os.environ['PROJECT_DATA_PATH'] = stage_example_data()
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if STAGED_ROOT not in sys.path:
+        sys.path.insert(0, STAGED_ROOT)
     import doppelspeller.settings as settings
     import doppelspeller.constants as constants
     import doppelspeller.common as common

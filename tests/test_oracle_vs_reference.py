@@ -138,3 +138,46 @@ def test_transform_title_random_unicode(ref):
             assert oracle.transform_title(title) == ref.common.transform_title(title), repr(title)
     finally:
         logging.disable(logging.NOTSET)
+
+
+def test_prematch_cascade_against_reference_prediction(ref, example):
+    """a6: oracle.prematch_ratio against the reference's own Prediction._get_levenshtein_ratio /
+    _get_levenshtein_deletion_ratio (predict.py:140-156), and the repo's host selection against the reference's
+    `> 94` / group-max / ambiguity drop (predict.py:158-176, run through pandas exactly as written there).
+    python-levenshtein's `ratio` itself stays a shim (third party, absent): what is pinned here is the cascade -
+    the float64 length pre-filter, the `<= 94` switch to the token-sorted ratio and the selection."""
+    import pandas as pd
+    from doppelspeller_b200 import predict as ours
+    c, s = ref.constants, ref.settings
+    prediction = ref.predict.Prediction
+    rng = np.random.default_rng(5)
+    truth_titles = list(example['truth'][c.COLUMN_TRANSFORMED_TITLE])
+    test_titles = list(example['test'][c.COLUMN_TRANSFORMED_TITLE])
+    rows, _, _ = oracle.topn(example['index'], 100)
+    pairs = [(test_titles[q], truth_titles[r]) for q in range(60) for r in rows[q]]
+    # near-identical pairs exercise the `ratio > 94` and the token-sort branches, word swaps only the latter
+    for title in truth_titles[:400]:
+        words = title.split()
+        pairs.append((title, title[:-1]))
+        pairs.append((title.replace('e', 'a', 1), title))
+        if len(words) > 1:
+            pairs.append((' '.join(words[::-1]), title))
+            pairs.append((' '.join(words[1:] + words[:1]) + 'x', title))
+    for _ in range(400):                                     # lengths around the pre-filter boundary (predict.py:150)
+        la = int(rng.integers(1, 120))
+        lb = max(1, int(round(la * rng.uniform(0.85, 1.0))))
+        pairs.append(('a' * la, 'a' * lb))
+    got = np.array([oracle.prematch_ratio(x, y) for x, y in pairs])
+    want = np.array([prediction._get_levenshtein_ratio(x, y) for x, y in pairs])
+    assert np.array_equal(got, want)
+    for x, y in pairs[::97]:
+        want_deletion = prediction._get_levenshtein_deletion_ratio(x, y)
+        assert ours.get_levenshtein_deletion_ratios([len(x)], [len(y)])[0] == want_deletion
+    # selection: the reference's own pandas statements on a frame of (test_index, ratio)
+    test_index = np.concatenate([np.repeat(np.arange(60), 100), 60 + rng.integers(0, 300, len(pairs) - 6000)])
+    frame = pd.DataFrame({c.COLUMN_TEST_INDEX: test_index, c.COLUMN_LEVENSHTEIN_RATIO: want})
+    matches = frame.loc[frame[c.COLUMN_LEVENSHTEIN_RATIO] > s.LEVENSHTEIN_RATIO_THRESHOLD, :]          # predict.py:172
+    is_max = matches.groupby([c.COLUMN_TEST_INDEX])[c.COLUMN_LEVENSHTEIN_RATIO].transform('max') == \
+        matches[c.COLUMN_LEVENSHTEIN_RATIO]                                                             # :173-174
+    kept = prediction._remove_duplicated_matches(matches.loc[is_max, :])                               # :176
+    assert np.array_equal(ours.select_close_matches(test_index, want), np.sort(kept.index.to_numpy()))
