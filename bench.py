@@ -1,21 +1,31 @@
 """bench.py - headline benchmark of the B200-native DoppelSpeller hot path.
 
-Workload (BASELINE.json configs[2], "C3"): synthetic 100,000 test titles x 500,000 truth titles of the
-example data set's length / trigram statistics, nearest-n = 10 IDF-weighted Jaccard top-n.  A "step" is
-one pass of the hot path over the whole query batch: every (query, truth) pair scored, the reference's
-selection rule applied, [Q, 10] candidate rows produced.
+Workloads (`--workload`, BASELINE.json configs):
+  c3          configs[2], the headline: synthetic 100,000 test x 500,000 truth titles with the example data set's word /
+              trigram statistics (doppelspeller_b200/synthetic.py), nearest-n = 10 IDF-weighted Jaccard top-n
+  c3-example  the same size grown from the REAL example titles (tests/golden/example_titles.npz tiled with typing edits)
+  c5          configs[4]: synthetic 1,000,000 x 10,000,000, truth rows sharded over the ranks (`--truth-shards N`)
+A "step" is one pass of the hot path over the whole query batch: every (query, truth) pair scored, the reference's
+selection rule applied, [Q, top_n] candidate rows produced.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c3-example|c5]
 
-`value`   whole-job titles/s with the query CSR already resident in HBM (device-timed, CUDA events,
-          max over ranks);  `e2e` the same through the public API with pinned HOST buffers (H2D of the
-          queries and D2H of the candidate rows inside the timed region).
-N > 1     (torchrun) the truth rows are sharded over the ranks; phases local -> all_gather -> merge
-          (doppelspeller_b200/sharded.py); total work is fixed -> "scaling": "strong".
---impl reference   times the CPU port of the reference path (oracle/, all host threads) on a bounded
-          sample of the same workload; rank 0 only.
+`value`   whole-job titles/s with the query CSR already resident in HBM (device-timed, CUDA events, max over ranks);
+`e2e`     the same through the public API with pinned HOST buffers (H2D of the queries and D2H of the candidate rows
+          inside the timed region).
+N > 1     (torchrun) 2-D layout: T truth shards (local scan -> all_gather -> merge, doppelspeller_b200/sharded.py) x
+          N / T independent query groups; total work is fixed -> "scaling": "strong".  Rank 0 checks a query sample
+          of the gathered result against the CPU oracle at every N.
+`extra`   (N = 1) the other BASELINE configs in the same record: c3-example, C4 (100M candidate pairs through the
+          InDel-ratio and the 66-feature kernels), the candidate pairs of the step, C1 / C2 (example data through the
+          drop-in classes, the reference's own numba path timed beside them).
+--impl reference   times the reference's own CPU implementation of the path on the host cores: the staged, unmodified
+          reference's numba kernels (oracle/_ref: match_maker.fast_jaccard + fast_arg_top_k driven like
+          get_closest_matches, match_maker.py:192-203) when staged, else the C / OpenMP port (oracle/ds_oracle.c);
+          each step a bounded query sample of the same workload; rank 0 only.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -28,9 +38,14 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = 'titles matched/sec vs 500k truth'
 UNIT = 'titles/s'
-
+WORKLOADS = {
+    'c3': dict(queries=100000, truth=500000, source='synthetic', tag='C3 (BASELINE.json configs[2])'),
+    'c3-example': dict(queries=100000, truth=500000, source='example', tag='C3 size, real example titles tiled'),
+    'c5': dict(queries=1000000, truth=10000000, source='synthetic', tag='C5 (BASELINE.json configs[4])'),
+}
+SMEM_PEAK_BYTES_PER_CLK_PER_SM = 128     # shared-memory crossbar (B300_MICROARCH.md, LDS/STS)
+N_SM = 148
 
 _STDOUT = None
 
@@ -45,15 +60,31 @@ def log(*args):
     print(*args, file=sys.stderr, flush=True)
 
 
-def build_workload(n_queries, n_truth):
-    from doppelspeller_b200 import encode, synthetic
-    t0 = time.time()
+def metric_name(n_truth):
+    if n_truth == 500000:
+        return 'titles matched/sec vs 500k truth'
+    return f'titles matched/sec vs {n_truth} truth'
+
+
+# ---------------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------------
+def make_titles(source, n_queries, n_truth):
+    """(truth titles, test titles): deterministic, identical on every rank."""
+    from doppelspeller_b200 import synthetic
+    if source == 'example':
+        raw = np.load(os.path.join(ROOT, 'tests', 'golden', 'example_titles.npz'))
+        truth = synthetic.tile_titles([str(t) for t in raw['truth_titles']], n_truth, synthetic.TRUTH_SEED)
+        test = synthetic.tile_titles([str(t) for t in raw['test_titles']], n_queries, synthetic.TEST_SEED)
+        return truth, test
     truth = synthetic.generate_truth_titles(n_truth)
     test, _ = synthetic.generate_test_titles(truth, n_queries)
-    enc = encode.encode_canonical(test, truth)
-    log(f'[bench] workload: {n_queries} test x {n_truth} truth titles, vocab {len(enc["idf64"])}, '
-        f'mean trigrams/truth title {np.diff(enc["t_ptr"]).mean():.2f} ({time.time() - t0:.1f}s)')
-    return truth, test, enc
+    return truth, test
+
+
+def encode_host(test, truth):
+    from doppelspeller_b200 import encode
+    return encode.encode_canonical(test, truth)
 
 
 def oracle_index(enc):
@@ -68,6 +99,14 @@ def cpu_sample(n_queries, size):
     return np.sort(rng.choice(n_queries, size=min(size, n_queries), replace=False))
 
 
+def host_threads():
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which must not throttle the CPU arm)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def time_cpu_port(index, sample, k):
     """The CPU port of match_maker.py:192-203 (oracle/ds_oracle.c, OpenMP over queries) on `sample`."""
     from oracle import oracle
@@ -76,12 +115,53 @@ def time_cpu_port(index, sample, k):
     return time.perf_counter() - t0, rows, count
 
 
-def host_threads():
-    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which must not throttle the CPU arm)."""
+class ReferenceKernels:
+    """The staged, unmodified reference's own numba kernels behind the data structures MatchMaker.__init__ builds
+    (match_maker.py:111-133), filled from the same encoded index the GPU arm uses."""
+
+    def __init__(self, index):
+        import numba
+        from oracle import ref_import
+        ref = ref_import.import_match_maker()
+        self.fast_jaccard = ref.match_maker.fast_jaccard
+        self.fast_arg_top_k = ref.match_maker.fast_arg_top_k
+        self.threads = min(host_threads(), numba.config.NUMBA_NUM_THREADS)
+        numba.set_num_threads(self.threads)
+        self.index = index
+        self.n_truth = int(index['n_truth'])
+        self.w64 = [float(x) for x in index['w64']]
+        post_ptr, post_rows, w32 = index['post_ptr'], index['post_rows'], index['w32']
+        columns = numba.typed.List()                                            # match_maker.py:122-133
+        for v in range(post_ptr.shape[0] - 1):
+            rows = np.ascontiguousarray(post_rows[post_ptr[v]:post_ptr[v + 1]], dtype=np.int32)
+            columns.append((rows, np.full(rows.shape[0], w32[v], dtype=np.float32)))
+        self.columns = columns
+        self.sums = np.ascontiguousarray(index['sums'], dtype=np.float32)
+
+    def closest_rows(self, q, k):
+        """MatchMaker.get_closest_matches (match_maker.py:192-203) up to the row indexes (the pandas title-id lookup of
+        :190 is left out on both arms)."""
+        nz = np.ascontiguousarray(self.index['qs_cols'][self.index['qs_ptr'][q]:self.index['qs_ptr'][q + 1]], dtype=np.int32)
+        mx = sum([self.w64[c] for c in nz])                                     # :197
+        scores = self.fast_jaccard(self.n_truth, mx, nz, self.columns, self.sums)   # :199
+        return self.fast_arg_top_k(scores, k)                                   # :187
+
+    def run(self, queries, k):
+        out = np.full((len(queries), k), -1, dtype=np.int64)
+        t0 = time.perf_counter()
+        for i, q in enumerate(queries):
+            rows = self.closest_rows(int(q), k)
+            out[i, :rows.shape[0]] = rows
+        return time.perf_counter() - t0, out
+
+
+def reference_staged():
     try:
-        return len(os.sched_getaffinity(0))
-    except AttributeError:
-        return os.cpu_count() or 1
+        from oracle import ref_import
+        import numba  # noqa: F401
+        return ref_import.reference_available()
+    except Exception:
+        return False
 
 
 class ClockSampler:
@@ -126,83 +206,123 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def measured_peak():
+def measured_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
-        return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
-    return 6650.0, 'fallback (B200_PROFILING.md)'
+        peaks = json.load(open(path))
+        return float(peaks['hbm_gbs']), float(peaks.get('sm_max_mhz', 1965.0)), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 1965.0, 'fallback (B200_PROFILING.md)'
 
 
-def committed_issue_utilisation(kernel):
-    """Issue-slot utilisation of `kernel` from the committed ncu capture (the real limiter of the K1 kernels)."""
-    import csv
-    path = os.path.join(ROOT, 'profiles', f'r1_{kernel}_metrics.csv')
+def source_id(*names):
+    digest = hashlib.sha256()
+    for name in names:
+        with open(os.path.join(ROOT, 'doppelspeller_b200', 'csrc', name), 'rb') as f:
+            digest.update(f.read())
+    return digest.hexdigest()[:16]
+
+
+def committed_ncu(kernel):
+    """profiles/r2_<kernel>_ncu.json: counters of the kernel from the committed `ncu --set full` capture (written by
+    profiles/summarize.py together with the hash of the kernel sources it was taken from)."""
+    path = os.path.join(ROOT, 'profiles', f'r2_{kernel}_ncu.json')
     if not os.path.exists(path):
         return None
-    for row in csv.reader(open(path)):
-        if row and row[0] == 'sm__inst_issued.avg.pct_of_peak_sustained_active':
-            values = [float(v) for v in row[2:] if v]
-            return sum(values) / len(values) / 100.0 if values else None
-    return None
+    return json.load(open(path))
 
 
-def committed_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture, if one has been summarised."""
-    path = os.path.join(ROOT, 'profiles', f'{kernel}_traffic.json')
-    if os.path.exists(path):
-        return json.load(open(path)).get('dram_bytes_per_launch')
-    return None
+def workload_config(args, stats):
+    spec = WORKLOADS.get(args.workload, {})
+    tag = spec.get('tag', 'custom size')
+    source = 'real example titles (tests/golden/example_titles.npz) tiled with typing edits' if args.source == 'example' else 'synthetic'
+    cfg = {'workload': f'{tag}: {source} {args.queries} test x {args.truth} truth titles, nearest-n={args.top_n} '
+                       f'IDF-weighted trigram Jaccard top-n',
+           'queries': args.queries, 'truth': args.truth, 'top_n': args.top_n,
+           'l2': 'flushed between timed steps (256 MiB memset, untimed)',
+           'layout': f'{args.n_shards} truth shard(s) (contiguous row ranges; all_gather + merge inside each group) x '
+                     f'{args.n_groups} query group(s)'}
+    cfg.update(stats)
+    return cfg
 
 
+def resolve_layout(args, world):
+    args.n_shards = args.truth_shards if args.truth_shards > 0 else min(world, 2)
+    if world % args.n_shards != 0:
+        raise SystemExit(f'--truth-shards {args.n_shards} must divide the number of ranks {world}')
+    args.n_groups = world // args.n_shards
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm
+# ---------------------------------------------------------------------------------------------------
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    from oracle import oracle
-    truth, test, enc = build_workload(args.queries, args.truth)
+    from doppelspeller_b200 import synthetic
+    resolve_layout(args, max(1, args.gpus))
+    truth, test = make_titles(args.source, args.queries, args.truth)
+    enc = encode_host(test, truth)
+    stats = synthetic.workload_statistics(enc)
     index = oracle_index(enc)
-    sample = cpu_sample(args.queries, args.cpu_sample)
-    for _ in range(args.warmup):
-        time_cpu_port(index, sample[:max(8, len(sample) // 16)], args.top_n)
-    times = [time_cpu_port(index, sample, args.top_n)[0] for _ in range(args.steps)]
-    per_step = float(np.mean(times))
-    value = len(sample) / per_step
+    k = args.top_n
     cores = host_threads()
-    line = {
-        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': per_step * 1e3, 'higher_is_better': True, 'scaling': 'strong',
-        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': workload_config(args, enc),
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                         'sample': f'{len(sample)} sampled queries x all {args.truth} truth rows per step, '
-                                   f'top-{args.top_n}; titles/s = sample / time (linear in Q)'},
-        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'gpu_launches': 0,
-    }
+    budget_s = 100.0 / max(1, args.steps + args.warmup)       # the whole run stays within a couple of minutes
+    line = {'impl': 'reference', 'metric': metric_name(args.truth), 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic' if args.source == 'synthetic' else 'example titles tiled', 'config': workload_config(args, stats),
+            'gpu_launches': 0}
+    port_sample = cpu_sample(args.queries, args.cpu_sample)
+    time_cpu_port(index, port_sample[:64], k)
+    port_s, port_rows, _ = time_cpu_port(index, port_sample, k)
+    port = {'value': len(port_sample) / port_s, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': f'{len(port_sample)} sampled queries x all {args.truth} truth rows, top-{k}'}
+    if reference_staged() and not args.port_only:
+        kernels = ReferenceKernels(index)
+        probe = cpu_sample(args.queries, 24)
+        kernels.run(probe[:4], k)                                # JIT compile (excluded, like SURVEY.md 8(d) says)
+        probe_s, _ = kernels.run(probe, k)
+        n_sample = int(max(16, min(len(port_sample), budget_s / (probe_s / len(probe)))))
+        sample = port_sample[:n_sample]
+        for _ in range(args.warmup):
+            kernels.run(sample[:max(4, n_sample // 8)], k)
+        times, rows = [], None
+        for _ in range(args.steps):
+            seconds, rows = kernels.run(sample, k)
+            times.append(seconds)
+        per_step = float(np.mean(times))
+        value = n_sample / per_step
+        line['cpu_baseline'] = {'value': value, 'unit': UNIT, 'cores': kernels.threads, 'kind': 'reference',
+                                'sample': f'{n_sample} sampled queries x all {args.truth} truth rows per step, top-{k}: the staged '
+                                          f'reference\'s numba fast_jaccard + fast_arg_top_k called like get_closest_matches '
+                                          f'(match_maker.py:192-203, JIT warm); titles/s = sample / time (linear in Q)',
+                                'port': port}
+        line['parity'] = {'reference_vs_port_checked_queries': n_sample,
+                          'reference_vs_port_mismatching_queries': int((rows != port_rows[:n_sample]).any(axis=1).sum())}
+    else:
+        sample = port_sample
+        for _ in range(args.warmup):
+            time_cpu_port(index, sample[:max(8, len(sample) // 16)], k)
+        times = [time_cpu_port(index, sample, k)[0] for _ in range(args.steps)]
+        per_step = float(np.mean(times))
+        value = len(sample) / per_step
+        line['cpu_baseline'] = dict(port, value=value)
+    line['value'] = value
+    # one step of the workload = all Q queries: per-step time extrapolated linearly in Q from the sample
+    line['ms_per_step'] = args.queries / value * 1e3
+    line['ms_per_sampled_step'] = per_step * 1e3
+    line['e2e'] = {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     emit(line)
 
 
-def workload_config(args, enc):
-    if (args.queries, args.truth) == (100000, 500000):
-        tag = 'C3 (BASELINE.json configs[2])'
-    elif (args.queries, args.truth) == (1000000, 10000000):
-        tag = 'C5 (BASELINE.json configs[4])'
-    else:
-        tag = 'custom size'
-    mean_g = float(enc['mean_g']) if 'mean_g' in enc else float(np.diff(enc['t_ptr']).mean())
-    return {'workload': f'{tag}: synthetic {args.queries} test x {args.truth} truth titles, nearest-n={args.top_n} '
-                        f'IDF-weighted trigram Jaccard top-n',
-            'queries': args.queries, 'truth': args.truth, 'top_n': args.top_n, 'vocab': int(len(enc['idf64'])),
-            'mean_trigrams_per_truth_title': mean_g,
-            'l2': 'flushed between timed steps (256 MiB memset, untimed)',
-            'shard': getattr(args, 'layout', 'truth rows, contiguous ranges')}
-
-
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from doppelspeller_b200 import _native as nat
-    from doppelspeller_b200 import sharded
+    from doppelspeller_b200 import encode, sharded, synthetic
     from doppelspeller_b200.index import TruthIndex
 
     rank = int(os.environ.get('RANK', '0'))
@@ -220,10 +340,8 @@ def run_ours(args):
     # ranks) and the queries are split over G = world / T such groups (independent, no collective between groups).
     # Default T = 2 for N >= 2: the index is sharded no further than memory asks for, but the NCCL merge path is
     # always exercised; --truth-shards N gives the fully truth-sharded layout of BASELINE configs[4].
-    n_shards = args.truth_shards if args.truth_shards > 0 else min(world, 2)
-    if world % n_shards != 0:
-        raise SystemExit(f'--truth-shards {n_shards} must divide the number of ranks {world}')
-    n_groups = world // n_shards
+    resolve_layout(args, world)
+    n_shards, n_groups = args.n_shards, args.n_groups
     group_id, shard_id = rank // n_shards, rank % n_shards
     subgroup = None
     if world > 1:
@@ -235,34 +353,34 @@ def run_ours(args):
     q0, q1 = int(q_offs[group_id]), int(q_offs[group_id + 1])
     n_q = q1 - q0
     offs = sharded.shard_offsets(n_truth, n_shards)
-    rank_shard = shard_id
-    if world > 1 or args.device_encode:
+
+    t0 = time.time()
+    truth, test = make_titles(args.source, n_q_total, n_truth)
+    t1 = time.time()
+    device_encoded = world > 1 or args.device_encode or n_truth > 2000000
+    if device_encoded:
         # index build entirely on the GPU (csrc/ds_encode.cu): trigram sets, canonical column ids, df, idf
-        from doppelspeller_b200 import encode, synthetic
-        t0 = time.time()
-        truth = synthetic.generate_truth_titles(n_truth)
-        test, _ = synthetic.generate_test_titles(truth, n_q_total)
-        t1 = time.time()
         dev_enc = encode.encode_canonical_device(test, truth, device=local_rank)
         torch.cuda.synchronize()
-        log(f'[bench] rank {rank}: titles generated in {t1 - t0:.1f}s, encoded on the GPU in {time.time() - t1:.2f}s '
-            f'(vocab {dev_enc["idf64"].shape[0]})')
-        ptr, cols = sharded.slice_truth_csr(dev_enc['t_ptr'], dev_enc['t_cols'], int(offs[rank_shard]), int(offs[rank_shard + 1]))
+        ptr, cols = sharded.slice_truth_csr(dev_enc['t_ptr'], dev_enc['t_cols'], int(offs[shard_id]), int(offs[shard_id + 1]))
         idf64 = dev_enc['idf64']
-        mean_g = float(dev_enc['t_cols'].shape[0]) / n_truth
-        enc = {'q_ptr': dev_enc['q_ptr'].cpu().numpy(), 'q_cols': dev_enc['q_cols'].cpu().numpy(), 'idf64': idf64.cpu().numpy(),
-               't_ptr': None, 'mean_g': mean_g}
-        del truth
+        enc = {'q_ptr': dev_enc['q_ptr'].cpu().numpy(), 'q_cols': dev_enc['q_cols'].cpu().numpy(), 'idf64': idf64.cpu().numpy()}
+        if rank == 0:       # host copy of the truth CSR: statistics and the oracle's parity sample
+            enc['t_ptr'], enc['t_cols'] = dev_enc['t_ptr'].cpu().numpy(), dev_enc['t_cols'].cpu().numpy()
+        del dev_enc
     else:
-        truth, test, enc = build_workload(n_q_total, n_truth)
-        ptr, cols = sharded.slice_truth_csr(enc['t_ptr'], enc['t_cols'], int(offs[rank_shard]), int(offs[rank_shard + 1]))
+        enc = encode_host(test, truth)
+        ptr, cols = sharded.slice_truth_csr(enc['t_ptr'], enc['t_cols'], int(offs[shard_id]), int(offs[shard_id + 1]))
         idf64 = enc['idf64']
-        enc['mean_g'] = float(np.diff(enc['t_ptr']).mean())
+    log(f'[bench] rank {rank}: titles in {t1 - t0:.1f}s, encoded ({"GPU" if device_encoded else "host"}) in {time.time() - t1:.1f}s, '
+        f'vocab {enc["idf64"].shape[0]}')
+    stats = synthetic.workload_statistics(enc) if rank == 0 else {}
     t0 = time.time()
-    index = TruthIndex(ptr, cols, idf64, device=local_rank, row_offset=int(offs[rank_shard]), n_total=n_truth)
+    index = TruthIndex(ptr, cols, idf64, device=local_rank, row_offset=int(offs[shard_id]), n_total=n_truth)
     torch.cuda.synchronize()
-    log(f'[bench] rank {rank}: truth rows [{offs[rank_shard]}, {offs[rank_shard + 1]}) x queries [{q0}, {q1}), index built in '
+    log(f'[bench] rank {rank}: truth rows [{offs[shard_id]}, {offs[shard_id + 1]}) x queries [{q0}, {q1}), index built in '
         f'{time.time() - t0:.2f}s')
+    del ptr, cols
 
     # this rank's query group
     my_q_ptr = np.ascontiguousarray(enc['q_ptr'][q0:q1 + 1] - enc['q_ptr'][q0])
@@ -275,9 +393,6 @@ def run_ours(args):
     h_count = torch.empty((n_q,), dtype=torch.int32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     shard = sharded.GpuShard(index, my_q_ptr, my_q_cols) if n_shards > 1 else None
-
-    args.layout = (f'{n_shards} truth shards (contiguous row ranges, all_gather + merge inside each group) x {n_groups} query groups'
-                   if world > 1 else 'single GPU')
     phase_ms = {} if os.environ.get('DS_PHASE_TIMING') else None
 
     def step_device():
@@ -344,74 +459,160 @@ def run_ours(args):
     h2d = int(n_shards * (enc['q_ptr'].nbytes + enc['q_cols'].nbytes))
     d2h = int(n_shards * (n_q_total * k * 8 + n_q_total * 4))
 
+    # the result of every query group on rank 0 (parity sample below): one padded all_gather over all ranks, the first
+    # rank of every group carries that group's rows
+    rows_all = rows
+    if world > 1:
+        max_q = int(np.diff(q_offs).max())
+        padded = torch.full((max_q, k), -1, dtype=torch.int64, device=device)
+        padded[:n_q] = rows
+        flat = torch.empty((world * max_q, k), dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(flat, padded)
+        if rank == 0:
+            rows_all = torch.cat([flat[g * n_shards * max_q: g * n_shards * max_q + int(q_offs[g + 1] - q_offs[g])]
+                                  for g in range(n_groups)], dim=0)
+        del flat, padded
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # roofline of the dominant kernel - k_post, the posting-list form of the K1 scan (k_scan, the dense form, only
-    # takes the first 4,096 rows and the fallbacks): algorithmic bytes = (query, truth) pairs x (2 * g_truth + 8) B
-    peak, peak_source = measured_peak()
-    bytes_per_pair = 2.0 * enc['mean_g'] + 8.0
+    hbm_peak, sm_mhz_max, peak_source = measured_peaks()
+    mean_g = stats['mean_trigrams_per_truth_title']
+    bytes_per_pair = 2.0 * mean_g + 8.0
     dominant = max(k1_profile, key=lambda name: k1_profile[name][0])
     scan_ms, scan_launches, scan_pairs = k1_profile[dominant]
-    achieved = scan_pairs * bytes_per_pair / (scan_ms / 1e3) / 1e9 if scan_ms > 0 else 0.0
-    roofline = {'bound': 'hbm', 'kernel': dominant, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': committed_traffic(dominant), 'peak_source': peak_source, 'algorithmic_bytes_per_pair': bytes_per_pair,
-                'launches': int(scan_launches), 'avg_launch_ms': scan_ms / max(1, scan_launches),
-                'kernel_share_of_step': scan_ms / total_ms if total_ms > 0 else None,
-                'issue_slot_utilisation_ncu': committed_issue_utilisation(dominant),
-                'k1_kernels': {name: {'ms_per_step': ms / args.steps, 'launches_per_step': n / args.steps,
-                                      'pair_share': pairs / max(1.0, sum(v[2] for v in k1_profile.values()))}
-                               for name, (ms, n, pairs) in k1_profile.items()},
-                'note': 'reporting convention of SURVEY.md 8(d) (bytes a dense scan of the CSR rows would read per pair); '
-                        'the index is L2 resident and k_post only touches the postings that hit a query, so frac > 1 is '
-                        'expected; the kernel is instruction-issue bound (see profiles/)'}
+    convention = scan_pairs * bytes_per_pair / (scan_ms / 1e3) / 1e9 if scan_ms > 0 else 0.0
+    roofline = build_roofline(dominant, scan_ms, scan_launches, total_ms, k1_profile, args.steps, convention, hbm_peak, peak_source,
+                              bytes_per_pair, sm_mhz_max, clocks)
 
     line = {
-        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'metric': metric_name(n_truth), 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
-        'data': 'synthetic', 'config': workload_config(args, enc), 'roofline': roofline,
+        'data': 'synthetic' if args.source == 'synthetic' else 'example titles tiled', 'config': workload_config(args, stats),
+        'roofline': roofline,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': e2e_ms / args.steps},
         'gpu_launches': int(gpu_launches), 'clocks': clocks,
     }
 
-    rows_np = rows.cpu().numpy() if hasattr(rows, 'cpu') else rows
+    rows_np = rows_all.cpu().numpy() if hasattr(rows_all, 'cpu') else rows_all
+    rows_mine = rows.cpu().numpy() if hasattr(rows, 'cpu') else rows
     e_rows_np = e_rows.numpy() if hasattr(e_rows, 'numpy') else e_rows
-    line['parity'] = {'e2e_equals_device_path': bool(np.array_equal(rows_np, e_rows_np))}
-    if world == 1 and not args.no_cpu and enc.get('t_ptr') is not None:
-        from oracle import oracle
+    line['parity'] = {'e2e_equals_device_path': bool(np.array_equal(rows_mine, e_rows_np))}
+    if not args.no_cpu:
+        # the parity gate of the run: a query sample of the (gathered, at N > 1) result against the CPU oracle
         index_cpu = oracle_index(enc)
-        sample = cpu_sample(n_q_total, args.cpu_sample)
+        sample = cpu_sample(n_q_total, args.cpu_sample if n_truth <= 2000000 else min(args.cpu_sample, 2000))
         time_cpu_port(index_cpu, sample[:64], k)
         seconds, want_rows, want_count = time_cpu_port(index_cpu, sample, k)
-        line['cpu_baseline'] = {'value': len(sample) / seconds, 'unit': UNIT, 'cores': host_threads(), 'kind': 'port',
-                                'sample': f'{len(sample)} sampled queries x all {n_truth} truth rows, top-{k}, '
-                                          f'{seconds:.1f}s; titles/s = sample / time (linear in Q)'}
-        line['parity'].update({'checked_queries': int(len(sample)),
+        port = {'value': len(sample) / seconds, 'unit': UNIT, 'cores': host_threads(), 'kind': 'port',
+                'sample': f'{len(sample)} sampled queries x all {n_truth} truth rows, top-{k}, {seconds:.1f}s; titles/s = sample / '
+                          f'time (linear in Q)'}
+        line['parity'].update({'checked_queries': int(len(sample)), 'checked_against': 'oracle/ds_oracle.c (CPU port)',
                                'mismatching_queries': int((rows_np[sample] != want_rows).any(axis=1).sum())})
-        line['extra'] = pair_kernels(truth, test, rows_np, device)
+        line['cpu_baseline'] = port
+        if world == 1 and reference_staged() and not args.no_extra:
+            try:
+                kernels = ReferenceKernels(index_cpu)
+                ref_sample = sample[:200 if n_truth <= 2000000 else 24]
+                kernels.run(ref_sample[:4], k)
+                ref_s, ref_rows = kernels.run(ref_sample, k)
+                line['cpu_baseline'] = {
+                    'value': len(ref_sample) / ref_s, 'unit': UNIT, 'cores': kernels.threads, 'kind': 'reference',
+                    'sample': f'{len(ref_sample)} sampled queries x all {n_truth} truth rows, top-{k}, {ref_s:.1f}s: the staged '
+                              f'reference\'s own numba fast_jaccard + fast_arg_top_k (match_maker.py:192-203, JIT warm)',
+                    'port': port}
+                line['parity']['reference_numba_checked_queries'] = int(len(ref_sample))
+                line['parity']['reference_numba_mismatching_queries'] = int((rows_np[ref_sample] != ref_rows).any(axis=1).sum())
+                del kernels
+            except Exception as error:   # the port stays the baseline
+                line['cpu_baseline']['reference_unavailable'] = repr(error)[:200]
+        del index_cpu
+    if world == 1 and not args.no_extra:
+        extra = {}
+        index.close()
+        del index
+        torch.cuda.empty_cache()
+        nat.check(nat.lib.ds_trim(local_rank))
+        for name, fn in (('candidate_pairs', lambda: pair_kernels(truth, test, rows_mine, device)),
+                         ('c3_example', lambda: second_workload(args, device)),
+                         ('c4', lambda: c4_pairs(device)),
+                         ('c1_c2', lambda: example_dropin(device))):
+            t0 = time.time()
+            try:
+                extra[name] = fn()
+            except Exception as error:
+                extra[name] = {'error': repr(error)[:300]}
+            extra[name]['wall_s'] = round(time.time() - t0, 1) if isinstance(extra[name], dict) else None
+            torch.cuda.empty_cache()
+            nat.check(nat.lib.ds_trim(local_rank))
+        line['extra'] = extra
     if world > 1:
         dist.destroy_process_group()
     emit(line)
 
 
+def build_roofline(dominant, scan_ms, scan_launches, total_ms, k1_profile, steps, convention, hbm_peak, peak_source, bytes_per_pair,
+                   sm_mhz_max, clocks):
+    """The dominant kernel against its MEASURED limiter.  The K1 kernels walk an L2-resident index (0.02 % DRAM
+    utilisation), so the limiter is taken from the committed `ncu --set full` capture of the current kernel sources
+    (profiles/r2_<kernel>_ncu.json): the busiest of shared-memory pipe / issue slots / DRAM.  The SURVEY.md 8(d) byte
+    convention (what a dense scan of the CSR rows would read) is kept as a labelled secondary figure."""
+    ncu = committed_ncu(dominant)
+    sm_mhz = (clocks or {}).get('sm_mhz') or sm_mhz_max
+    smem_peak = N_SM * SMEM_PEAK_BYTES_PER_CLK_PER_SM * sm_mhz * 1e6 / 1e9        # GB/s at the clock seen under load
+    out = {'kernel': dominant, 'launches': int(scan_launches), 'avg_launch_ms': scan_ms / max(1, scan_launches),
+           'kernel_share_of_step': scan_ms / total_ms if total_ms > 0 else None,
+           'k1_kernels': {name: {'ms_per_step': ms / steps, 'launches_per_step': n / steps,
+                                 'pair_share': pairs / max(1.0, sum(v[2] for v in k1_profile.values()))}
+                          for name, (ms, n, pairs) in k1_profile.items()},
+           'hbm_convention': {'what': 'SURVEY.md 8(d): (query, truth) pairs x (2 * mean trigrams + 8) B over the kernel time - the '
+                                      'bytes a dense scan of the truth CSR would read; the index is L2 resident and the kernel only '
+                                      'touches the postings that hit a query, so this exceeds the HBM peak by construction',
+                              'achieved_gbs': convention, 'peak_gbs': hbm_peak, 'frac': convention / hbm_peak,
+                              'algorithmic_bytes_per_pair': bytes_per_pair, 'peak_source': peak_source}}
+    if ncu is None:
+        out.update({'bound': 'hbm', 'achieved': convention, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': convention / hbm_peak,
+                    'traffic': None, 'note': 'no committed ncu capture of this kernel: byte convention only'})
+        return out
+    limiters = {'shared-memory pipe': ncu.get('smem_wavefronts_pct'), 'issue slots': ncu.get('issue_active_pct'),
+                'hbm': ncu.get('dram_throughput_pct')}
+    bound = max((name for name in limiters if limiters[name] is not None), key=lambda name: limiters[name])
+    frac = limiters[bound] / 100.0
+    current = source_id('ds_topn.cu', 'ds_common.cuh')
+    if bound == 'shared-memory pipe':
+        peak, unit = smem_peak, 'GB/s'
+    elif bound == 'hbm':
+        peak, unit = hbm_peak, 'GB/s'
+    else:
+        peak, unit = N_SM * 4 * sm_mhz * 1e6 / 1e9, 'G warp-instructions/s'
+    out.update({'bound': bound, 'achieved': frac * peak, 'peak': peak, 'unit': unit, 'frac': frac,
+                'traffic': ncu.get('dram_bytes_per_launch'),
+                'ncu': {k_: ncu.get(k_) for k_ in ('smem_wavefronts_pct', 'issue_active_pct', 'dram_throughput_pct', 'warps_active_pct',
+                                                   'lsu_pipe_pct', 'l2_bytes_per_launch', 'dram_bytes_per_launch', 'captured_launch_ms',
+                                                   'registers', 'workload')},
+                'ncu_source': ncu.get('source'), 'ncu_kernel_sources': ncu.get('kernel_sources'),
+                'ncu_matches_current_sources': ncu.get('kernel_sources') == current,
+                'note': 'frac = utilisation of the measured limiter (ncu, profiles/); peak = that unit\'s peak at the SM clock '
+                        'sampled during the timed region; launch times and shares are measured live with CUDA events'})
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# extras (N = 1): the other BASELINE configs in the same record
+# ---------------------------------------------------------------------------------------------------
 def pair_kernels(truth, test, rows, device):
-    """Secondary metrics (BASELINE.json: "Levenshtein pairs/sec"): K2 InDel ratio and K3 66-feature kernels on
-    the candidate pairs of the step (compact title tables resident in HBM)."""
+    """K2 InDel ratio and K3 66-feature kernels on the candidate pairs of the step (compact title tables resident in
+    HBM), and the whole hot path as one GPU-resident pass."""
     import torch
-    from collections import Counter
     from doppelspeller_b200 import _native as nat
     from doppelspeller_b200 import feature_engineering as fe
+    from doppelspeller_b200 import pipeline as pl
     n_q, k = rows.shape
     codes_a, off_a = fe.encode_titles(test)
     codes_b, off_b = fe.encode_titles(truth)
-    counter = Counter(w for t in truth for w in set(t.split()))
-    counts = np.zeros((len(truth), 15), dtype=np.uint32)
-    for i, t in enumerate(truth):
-        ws = [counter[w] for w in t.split()[:15]]
-        counts[i, :len(ws)] = ws
+    counts = pl.truth_word_counts(truth)
     dev = lambda x: torch.as_tensor(x).to(device)   # noqa: E731
     d = dict(a=dev(codes_a), oa=dev(off_a), b=dev(codes_b), ob=dev(off_b), c=dev(counts.view(np.int32)),
              ia=dev(np.repeat(np.arange(n_q, dtype=np.int32), k)), ib=dev(rows.reshape(-1).astype(np.int32)))
@@ -431,6 +632,7 @@ def pair_kernels(truth, test, rows, device):
     out = {}
     la = np.diff(off_a)[np.repeat(np.arange(n_q), k)]
     lb = np.diff(off_b)[rows.reshape(-1)]
+    hbm_peak = measured_peaks()[0]
     for name, fn, bytes_per_pair in (('indel_ratio', run_ratio, float((la + lb).mean()) + 3.0),
                                      ('construct_features', run_feats, float((la + lb).mean()) + 2.0 + 60.0 + 264.0)):
         for _ in range(3):
@@ -443,13 +645,11 @@ def pair_kernels(truth, test, rows, device):
         stop.record()
         stop.synchronize()
         ms = start.elapsed_time(stop) / 3
-        peak, _ = measured_peak()
         out[name] = {'pairs_per_s': n / (ms / 1e3), 'pairs': n, 'ms': ms, 'algorithmic_bytes_per_pair': bytes_per_pair,
-                     'hbm_frac': n * bytes_per_pair / (ms / 1e3) / 1e9 / peak}
+                     'hbm_frac': n * bytes_per_pair / (ms / 1e3) / 1e9 / hbm_peak}
     # the whole hot path as one GPU-resident pass (north_star target: "100k test titles matched, nearest-n Jaccard +
     # Levenshtein features, against 500k truth titles"): host title strings in, candidate rows + features out
-    from doppelspeller_b200.pipeline import CandidatePipeline
-    pipeline = CandidatePipeline(truth, device=device.index)
+    pipeline = pl.CandidatePipeline(truth, device=device.index)
     for _ in range(2):
         pipeline.run(test, k)
     torch.cuda.synchronize()
@@ -463,21 +663,80 @@ def pair_kernels(truth, test, rows, device):
     return out
 
 
+def second_workload(args, device):
+    """The headline measurement repeated on the workload grown from the real example titles (density is the data
+    set's own, not the generator's)."""
+    import torch
+    from doppelspeller_b200 import synthetic
+    from doppelspeller_b200.index import TruthIndex
+    source = 'example' if args.source == 'synthetic' else 'synthetic'
+    n_q, n_truth, k = args.queries, args.truth, args.top_n
+    truth, test = make_titles(source, n_q, n_truth)
+    enc = encode_host(test, truth)
+    stats = synthetic.workload_statistics(enc)
+    index = TruthIndex(enc['t_ptr'], enc['t_cols'], enc['idf64'], device=device.index)
+    d_q_ptr, d_q_cols = torch.as_tensor(enc['q_ptr']).to(device), torch.as_tensor(enc['q_cols']).to(device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    for _ in range(3):
+        rows, _ = index.topn(d_q_ptr, d_q_cols, k)
+    times = []
+    for _ in range(5):
+        flush.zero_()
+        torch.cuda.synchronize()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        rows, _ = index.topn(d_q_ptr, d_q_cols, k)
+        stop.record()
+        stop.synchronize()
+        times.append(start.elapsed_time(stop))
+    ms = float(np.mean(times))
+    index_cpu = oracle_index(enc)
+    sample = cpu_sample(n_q, 5000)
+    _, want_rows, _ = time_cpu_port(index_cpu, sample, k)
+    got = rows.cpu().numpy()
+    index.close()
+    return {'workload': ('real example titles tiled with typing edits' if source == 'example' else 'synthetic') +
+            f', {n_q} x {n_truth}, top-{k}', 'value': n_q / (ms / 1e3), 'unit': UNIT, 'ms_per_step': ms, 'steps': 5, 'statistics': stats,
+            'parity': {'checked_queries': int(len(sample)), 'mismatching_queries': int((got[sample] != want_rows).any(axis=1).sum())}}
+
+
+def c4_pairs(device):
+    """BASELINE configs[3]: 100M synthetic candidate pairs, titles up to 128 characters (bench_pairs.py)."""
+    import bench_pairs
+    return bench_pairs.run(pairs=100_000_000, titles=400_000, steps=2, sample=100_000, chunk=25_000_000, device=device)
+
+
+def example_dropin(device):
+    """BASELINE configs[0] / [1] on the example data: the drop-in classes driven like Prediction drives them, each stage
+    timed beside the staged reference's own code on the host (oracle/_ref; numba JIT warm)."""
+    import bench_example
+    return bench_example.run(device)
+
+
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument('--gpus', type=int, default=1)
     parser.add_argument('--steps', type=int, default=3)
     parser.add_argument('--warmup', type=int, default=3)
     parser.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    parser.add_argument('--queries', type=int, default=100000)
-    parser.add_argument('--truth', type=int, default=500000)
+    parser.add_argument('--workload', default='c3', choices=sorted(WORKLOADS))
+    parser.add_argument('--queries', type=int, default=0, help='override the workload\'s query count')
+    parser.add_argument('--truth', type=int, default=0, help='override the workload\'s truth row count')
     parser.add_argument('--top-n', type=int, default=10)
     parser.add_argument('--cpu-sample', type=int, default=20000)
     parser.add_argument('--truth-shards', type=int, default=0,
                         help='ranks the truth rows are sharded over (0 = auto: 2 when N >= 2); queries are split over N / T groups')
     parser.add_argument('--device-encode', action='store_true', help='build the index with the GPU encoder also at N=1')
     parser.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline / parity sample (profiling runs)')
+    parser.add_argument('--no-extra', action='store_true', help='skip the secondary workloads of the N = 1 record')
+    parser.add_argument('--port-only', action='store_true', help='--impl reference: time the C port even when the reference is staged')
     args = parser.parse_args()
+    spec = WORKLOADS[args.workload]
+    args.queries = args.queries or spec['queries']
+    args.truth = args.truth or spec['truth']
+    args.source = spec['source']
+    if args.no_cpu:
+        args.no_extra = True
     # stdout must carry exactly one JSON line: libraries that print to fd 1 (NCCL's version banner) are
     # diverted to stderr, the JSON goes to the original stdout
     global _STDOUT

@@ -1,0 +1,155 @@
+"""bench_example.py - BASELINE.json configs[0] (C1: example generate-predictions path, 10,000 test x 30,000 truth titles,
+top_n = 100) and configs[1] (C2: closest-search-single-title, one query against the whole truth DB) on the example data.
+
+The drop-in classes are driven exactly like `Prediction` drives the reference's (DataFrames from the reference's own
+CSV reader, one `get_closest_matches` call per row, `construct_features` with the gufunc signature) and every stage is
+timed beside the staged, unmodified reference's own code on the host cores (oracle/_ref; numba JIT warm):
+
+    index build      MatchMaker.__init__                    match_maker.py:84-109
+    candidates       [get_closest_matches(q) for q in rows] match_maker.py:192-203, predict.py:126-127
+    pre-match ratio  Prediction._get_levenshtein_ratio       predict.py:140-156 (python-levenshtein's ratio restated in C)
+    features         construct_features                      feature_engineering.py:75-169, predict.py:216-219
+
+The end-to-end swap itself (the reference's Prediction.generate_test_predictions with three imports replaced) is
+tests/test_gpu_dropin.py; this file is the timing.  `python bench_example.py` prints one JSON line; bench.py embeds the
+same dict as `extra.c1_c2`.
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TOP_N = 100                      # settings.py:56 TOP_N_RESULTS_TO_FIND_FOR_PREDICTING
+SINGLE_TITLE = 'graet expectatoins minstries intl'
+
+
+def _timed(fn, repeat=1):
+    best, out = None, None
+    for _ in range(repeat):
+        t0 = time.perf_counter()
+        out = fn()
+        seconds = time.perf_counter() - t0
+        best = seconds if best is None else min(best, seconds)
+    return best, out
+
+
+def run(device=None, reference_rows=1000, reference_pairs=60000, feature_queries=2000):
+    import torch
+    from oracle import dropin
+    from doppelspeller_b200 import feature_engineering as fe
+    from doppelspeller_b200 import predict as ours_predict
+    from doppelspeller_b200.match_maker import MatchMaker
+    if device is not None:
+        torch.cuda.set_device(device)
+    ref = dropin.load_reference()
+    c = ref.constants
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    truth = ref.common.get_ground_truth()
+    test = ref.common.get_test_data()
+    n_q, n_truth = len(test), len(truth)
+    out = {'config': f'example data: {n_q} test x {n_truth} truth titles, top_n = {TOP_N}', 'host_cores': cores}
+
+    # ---- C1: index build + candidates ----
+    build_s, mm = _timed(lambda: MatchMaker(test.copy(), truth.copy(), TOP_N))
+    loop_first_s, _ = _timed(lambda: mm.get_closest_matches(0))                  # the first call computes every row on the GPU
+    loop_s, ours_ids = _timed(lambda: [mm.get_closest_matches(q) for q in range(n_q)])
+    canon_s, mm_canon = _timed(lambda: MatchMaker(test.copy(), truth.copy(), TOP_N, order='canonical'))
+    canon_first_s, _ = _timed(lambda: mm_canon.get_closest_matches(0))
+    ref_build_s, ref_mm = _timed(lambda: ref.match_maker.MatchMaker(test.copy(), truth.copy(), TOP_N))
+    ref_mm.get_closest_matches(0)                                                # numba JIT (excluded)
+    sample = np.linspace(0, n_q - 1, reference_rows).astype(np.int64)
+    ref_loop_s, ref_ids = _timed(lambda: [ref_mm.get_closest_matches(int(q)) for q in sample])
+    out['c1_candidates'] = {
+        'ours': {'index_build_s': build_s, 'scan_all_rows_s': loop_first_s, 'per_row_calls_s': loop_s,
+                 'titles_per_s': n_q / (build_s + loop_first_s + loop_s), 'titles_per_s_without_build': n_q / (loop_first_s + loop_s),
+                 'canonical_order_index_build_s': canon_s, 'canonical_order_scan_all_rows_s': canon_first_s},
+        'reference': {'index_build_s': ref_build_s, 'sampled_rows': int(len(sample)), 'per_row_calls_s': ref_loop_s,
+                      'titles_per_s_without_build': len(sample) / ref_loop_s,
+                      'titles_per_s': n_q / (ref_build_s + ref_loop_s * n_q / len(sample)), 'kind': 'reference', 'cores': cores},
+        'parity': {'checked_rows': int(len(sample)),
+                   'mismatching_rows': int(sum(1 for i, q in enumerate(sample) if ours_ids[int(q)] != ref_ids[i]))}}
+
+    # ---- C1: pre-match ratios of the (title, candidate) pairs ----
+    titles = list(test[c.COLUMN_TRANSFORMED_TITLE])
+    truth_title_of = dict(zip(truth[c.COLUMN_TITLE_ID], truth[c.COLUMN_TRANSFORMED_TITLE]))
+    pair_titles = [titles[q] for q in range(n_q) for _ in range(TOP_N)]
+    pair_matches = [truth_title_of[t] for q in range(n_q) for t in ours_ids[q]]
+    ratio_s, ours_ratios = _timed(lambda: ours_predict.get_levenshtein_ratios(pair_titles, pair_matches))
+    picked = np.linspace(0, len(pair_titles) - 1, reference_pairs).astype(np.int64)
+    get_ratio = ref.predict.Prediction._get_levenshtein_ratio
+    ref_ratio_s, ref_ratios = _timed(lambda: [get_ratio(pair_titles[i], pair_matches[i]) for i in picked])
+    out['c1_prematch'] = {
+        'ours': {'pairs': len(pair_titles), 'seconds': ratio_s, 'pairs_per_s': len(pair_titles) / ratio_s},
+        'reference': {'sampled_pairs': int(len(picked)), 'seconds': ref_ratio_s, 'pairs_per_s': len(picked) / ref_ratio_s,
+                      'kind': 'reference cascade over the restated python-levenshtein ratio (C)', 'cores': 1},
+        'parity': {'checked_pairs': int(len(picked)),
+                   'mismatching_pairs': int((ours_ratios[picked] != np.array(ref_ratios)).sum())}}
+
+    # ---- C1: construct_features with the reference's gufunc signature (predict.py:195-219) ----
+    fq = np.linspace(0, n_q - 1, feature_queries).astype(np.int64)
+    f_idx = (fq[:, None] * TOP_N + np.arange(TOP_N)[None, :]).reshape(-1)
+    f_titles = [pair_titles[i] for i in f_idx]
+    f_matches = [pair_matches[i] for i in f_idx]
+    words_counter = ref.common.get_words_counter(truth)
+    la = np.array([len(t) for t in f_titles], dtype=np.uint8)
+    lb = np.array([len(t) for t in f_matches], dtype=np.uint8)
+    enc_a = np.vstack([fe.encode_title(t) for t in f_titles])
+    enc_b = np.vstack([fe.encode_title(t) for t in f_matches])
+    counts = np.vstack([fe.get_truth_words_counts(t, words_counter) for t in f_matches])
+    dummy = np.zeros((fe.FEATURES_COUNT,), dtype=np.uint8)
+
+    def ours_features():
+        response = np.zeros((len(f_idx), fe.FEATURES_COUNT), dtype=np.float32)
+        fe.construct_features(la, lb, enc_a, enc_b, counts, fe.SPACE_CODE, n_truth, dummy, response)
+        return response
+
+    def reference_features():
+        response = np.zeros((len(f_idx), fe.FEATURES_COUNT), dtype=np.float32)
+        with np.errstate(all='ignore'):
+            ref.feature_engineering.construct_features(la, lb, enc_a, enc_b, counts, np.uint8(fe.SPACE_CODE), np.uint32(n_truth), dummy,
+                                                       response)
+        return response
+    ours_features()
+    feat_s, got = _timed(ours_features, repeat=2)
+    reference_features()                                                        # gufunc already compiled at import; warm caches
+    ref_feat_s, want = _timed(reference_features)
+    exact = (got[:, :36] == want[:, :36]) | (np.isnan(got[:, :36]) & np.isnan(want[:, :36]))
+    with np.errstate(all='ignore'):
+        close = np.isclose(got[:, 36:], want[:, 36:], rtol=1e-6, atol=0, equal_nan=True)
+    out['c1_features'] = {
+        'ours': {'pairs': int(len(f_idx)), 'seconds': feat_s, 'pairs_per_s': len(f_idx) / feat_s,
+                 'what': 'host [P, 255] arrays in, host [P, 66] out (the gufunc call of predict.py:216-219; copies included)'},
+        'reference': {'pairs': int(len(f_idx)), 'seconds': ref_feat_s, 'pairs_per_s': len(f_idx) / ref_feat_s, 'kind': 'reference',
+                      'cores': cores},
+        'parity': {'checked_pairs': int(len(f_idx)), 'integer_feature_mismatches': int((~exact).sum()),
+                   'float_feature_mismatches': int((~close).sum())}}
+
+    # ---- C2: one title against the whole truth DB (cli.py:64-83) ----
+    one = ref.common.get_data_for_one_title(SINGLE_TITLE)
+
+    def ours_single(order):
+        single = MatchMaker(one.copy(), truth.copy(), TOP_N, order=order)
+        return single.get_closest_matches(0)
+
+    def reference_single():
+        single = ref.match_maker.MatchMaker(one.copy(), truth.copy(), TOP_N)
+        return single.get_closest_matches(0)
+    ours_single('reference')
+    single_s, single_ids = _timed(lambda: ours_single('reference'), repeat=2)
+    single_canon_s, _ = _timed(lambda: ours_single('canonical'), repeat=2)
+    ref_single_s, ref_single_ids = _timed(reference_single)
+    out['c2_single_title'] = {
+        'ours': {'latency_s': single_s, 'canonical_order_latency_s': single_canon_s,
+                 'what': 'MatchMaker(one row, truth, 100) + get_closest_matches(0): index build included, like the CLI command'},
+        'reference': {'latency_s': ref_single_s, 'kind': 'reference', 'cores': cores},
+        'parity': {'same_candidates': bool(single_ids == ref_single_ids)}}
+    return out
+
+
+if __name__ == '__main__':
+    print(json.dumps(run(0)), flush=True)

@@ -15,7 +15,6 @@ import json
 import os
 import sys
 import time
-from collections import Counter
 
 import numpy as np
 
@@ -35,45 +34,35 @@ def build_pairs(n_pairs, n_titles):
     return truth, test, idx_a, idx_b
 
 
-def main():
-    parser = argparse.ArgumentParser()
-    parser.add_argument('--pairs', type=int, default=100_000_000)
-    parser.add_argument('--titles', type=int, default=400_000)
-    parser.add_argument('--steps', type=int, default=3)
-    parser.add_argument('--sample', type=int, default=200_000)
-    parser.add_argument('--chunk', type=int, default=25_000_000, help='pairs per kernel launch (bounds the 264 B/pair output)')
-    args = parser.parse_args()
+def run(pairs=100_000_000, titles=400_000, steps=3, sample=200_000, chunk=25_000_000, device=None):
     import torch
     from doppelspeller_b200 import _native as nat
     from doppelspeller_b200 import feature_engineering as fe
+    from doppelspeller_b200 import pipeline as pl
     from oracle import oracle
-    device = torch.device('cuda', 0)
+    device = torch.device('cuda', 0) if device is None else device
     t0 = time.time()
-    truth, test, idx_a, idx_b = build_pairs(args.pairs, args.titles)
-    counter = Counter(w for t in truth for w in set(t.split()))
-    counts = np.zeros((len(truth), 15), dtype=np.uint32)
-    for i, t in enumerate(truth):
-        ws = [counter[w] for w in t.split()[:15]]
-        counts[i, :len(ws)] = ws
+    truth, test, idx_a, idx_b = build_pairs(pairs, titles)
+    counts = pl.truth_word_counts(truth)
     codes_a, off_a = fe.encode_titles(test)
     codes_b, off_b = fe.encode_titles(truth)
-    print(f'[bench_pairs] {args.pairs} pairs over {len(test)} + {len(truth)} titles built in {time.time() - t0:.1f}s', file=sys.stderr)
+    print(f'[bench_pairs] {pairs} pairs over {len(test)} + {len(truth)} titles built in {time.time() - t0:.1f}s', file=sys.stderr)
     dev = lambda x: torch.as_tensor(x).to(device)   # noqa: E731
     d = dict(a=dev(codes_a), oa=dev(off_a), b=dev(codes_b), ob=dev(off_b), c=dev(counts.view(np.int32)), ia=dev(idx_a), ib=dev(idx_b))
     la = np.diff(off_a)[idx_a[:2_000_000]]
     lb = np.diff(off_b)[idx_b[:2_000_000]]
     mean_len = float((la + lb).mean())
-    chunk = min(args.chunk, args.pairs)
-    ratio = torch.empty(args.pairs, dtype=torch.uint8, device=device)
+    chunk = min(chunk, pairs)
+    ratio = torch.empty(pairs, dtype=torch.uint8, device=device)
     feats = torch.empty((chunk, 66), dtype=torch.float32, device=device)
 
     def run_ratio():
         nat.check(nat.lib.ds_indel_ratio_pairs(nat.ptr(d['a']), nat.ptr(d['oa']), len(test), nat.ptr(d['b']), nat.ptr(d['ob']), len(truth),
-                                               nat.ptr(d['ia']), nat.ptr(d['ib']), args.pairs, nat.ptr(ratio), None, nat.current_stream()))
+                                               nat.ptr(d['ia']), nat.ptr(d['ib']), pairs, nat.ptr(ratio), None, nat.stream_for(ratio)))
 
     def run_feats():
-        for c0 in range(0, args.pairs, chunk):
-            c1 = min(args.pairs, c0 + chunk)
+        for c0 in range(0, pairs, chunk):
+            c1 = min(pairs, c0 + chunk)
             fe.construct_features_pairs((d['a'], d['oa']), (d['b'], d['ob']), d['c'], d['ia'][c0:c1], d['ib'][c0:c1], fe.SPACE_CODE,
                                         len(truth), response=feats[:c1 - c0])
 
@@ -81,31 +70,30 @@ def main():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
         peak = float(json.load(open(path))['hbm_gbs'])
-    line = {'metric': 'Levenshtein pairs/sec', 'unit': 'pairs/s', 'pairs': args.pairs, 'data': 'synthetic',
-            'config': {'workload': f'C4 synthetic {args.pairs} candidate pairs, 10% titles in [65,128] chars (BASELINE.json configs[3])',
+    line = {'metric': 'Levenshtein pairs/sec', 'unit': 'pairs/s', 'pairs': pairs, 'data': 'synthetic',
+            'config': {'workload': f'C4 synthetic {pairs} candidate pairs, 10% titles in [65,128] chars (BASELINE.json configs[3])',
                        'mean_la_plus_lb': mean_len}}
     for name, fn, bpp in (('indel_ratio', run_ratio, mean_len + 3.0), ('construct_features', run_feats, mean_len + 2.0 + 60.0 + 264.0)):
         fn()
         torch.cuda.synchronize()
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
-        for _ in range(args.steps):
+        for _ in range(steps):
             fn()
         stop.record()
         stop.synchronize()
-        ms = start.elapsed_time(stop) / args.steps
-        line[name] = {'pairs_per_s': args.pairs / (ms / 1e3), 'ms': ms, 'algorithmic_bytes_per_pair': bpp,
-                      'hbm_frac': args.pairs * bpp / (ms / 1e3) / 1e9 / peak}
+        ms = start.elapsed_time(stop) / steps
+        achieved = pairs * bpp / (ms / 1e3) / 1e9
+        line[name] = {'pairs_per_s': pairs / (ms / 1e3), 'ms': ms, 'algorithmic_bytes_per_pair': bpp, 'hbm_frac': achieved / peak,
+                      'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                                   'traffic': None}}
     # parity of a sample against the oracle (padded layout on the CPU side)
-    n = min(args.sample, args.pairs, chunk)
+    n = min(sample, pairs, chunk)
     sel = np.arange(n)
-    pa = np.zeros((n, 255), dtype=np.uint8)
-    pb = np.zeros((n, 255), dtype=np.uint8)
     la_s = np.diff(off_a)[idx_a[sel]].astype(np.uint8)
     lb_s = np.diff(off_b)[idx_b[sel]].astype(np.uint8)
-    for i in range(n):
-        pa[i, :la_s[i]] = codes_a[off_a[idx_a[i]]:off_a[idx_a[i] + 1]]
-        pb[i, :lb_s[i]] = codes_b[off_b[idx_b[i]]:off_b[idx_b[i] + 1]]
+    pa = _padded_rows(codes_a, off_a, idx_a[sel])
+    pb = _padded_rows(codes_b, off_b, idx_b[sel])
     want_ratio = oracle.indel_ratio_u8_batch(pa, pb, la_s, lb_s)
     want_feats = oracle.construct_features(la_s, lb_s, pa, pb, counts[idx_b[sel]], fe.SPACE_CODE, len(truth))
     run_feats_first = fe.construct_features_pairs((d['a'], d['oa']), (d['b'], d['ob']), d['c'], d['ia'][:n], d['ib'][:n], fe.SPACE_CODE,
@@ -125,11 +113,32 @@ def main():
     t0 = time.perf_counter()
     oracle.construct_features(la_s, lb_s, pa, pb, counts[idx_b[sel]], fe.SPACE_CODE, len(truth), n_threads=cores)
     t_feat = time.perf_counter() - t0
-    line['cpu_baseline'] = {'kind': 'port', 'cores': cores, 'sample': f'the first {n} pairs of the batch',
-                            'indel_ratio_pairs_per_s': n / t_ratio, 'construct_features_pairs_per_s': n / t_feat}
+    line['cpu_baseline'] = {'kind': 'port', 'cores': cores, 'sample': f'the first {n} pairs of the batch', 'unit': 'pairs/s',
+                            'value': n / t_feat, 'indel_ratio_pairs_per_s': n / t_ratio, 'construct_features_pairs_per_s': n / t_feat}
     line['parity'] = {'sampled_pairs': int(n), 'ratio_mismatches': int((got_ratio != want_ratio).sum()),
                       'integer_feature_mismatches': int((~exact).sum()), 'float_feature_mismatches': int((~close).sum())}
-    print(json.dumps(line), flush=True)
+    return line
+
+
+def _padded_rows(codes, offsets, index):
+    """[n, 255] zero padded code rows of the titles `index` (the reference's layout, predict.py:199-204), vectorised."""
+    lengths = (offsets[index + 1] - offsets[index]).astype(np.int64)
+    out = np.zeros((index.shape[0], 255), dtype=np.uint8)
+    row_of = np.repeat(np.arange(index.shape[0]), lengths)
+    col_of = np.arange(int(lengths.sum())) - np.repeat(np.cumsum(lengths) - lengths, lengths)
+    out[row_of, col_of] = codes[np.repeat(offsets[index], lengths) + col_of]
+    return out
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--pairs', type=int, default=100_000_000)
+    parser.add_argument('--titles', type=int, default=400_000)
+    parser.add_argument('--steps', type=int, default=3)
+    parser.add_argument('--sample', type=int, default=200_000)
+    parser.add_argument('--chunk', type=int, default=25_000_000, help='pairs per kernel launch (bounds the 264 B/pair output)')
+    args = parser.parse_args()
+    print(json.dumps(run(args.pairs, args.titles, args.steps, args.sample, args.chunk)), flush=True)
 
 
 if __name__ == '__main__':

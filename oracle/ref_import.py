@@ -81,9 +81,7 @@ def stage_example_data():
     return target
 
 
-def import_reference():
-    """Returns the imported reference modules as a namespace (common, match_maker, feature_engineering,
-    predict, settings, constants)."""
+def _prepare():
     if not reference_available():
         raise RuntimeError('the reference is not staged under oracle/_ref (run oracle/stage_reference.py in the build container)')
     if 'Levenshtein' not in sys.modules:
@@ -95,6 +93,22 @@ def import_reference():
     os.environ['PROJECT_DATA_PATH'] = stage_example_data()
     if STAGED_ROOT not in sys.path:
         sys.path.insert(0, STAGED_ROOT)
+
+
+def import_match_maker():
+    """Only settings / constants / common / match_maker (skips feature_engineering's eager 11 s gufunc compile)."""
+    _prepare()
+    import doppelspeller.settings as settings
+    import doppelspeller.constants as constants
+    import doppelspeller.common as common
+    import doppelspeller.match_maker as match_maker
+    return types.SimpleNamespace(settings=settings, constants=constants, common=common, match_maker=match_maker)
+
+
+def import_reference():
+    """Returns the imported reference modules as a namespace (common, match_maker, feature_engineering,
+    predict, settings, constants)."""
+    _prepare()
     import doppelspeller.settings as settings
     import doppelspeller.constants as constants
     import doppelspeller.common as common
