@@ -24,6 +24,7 @@
 // the score matrix never exists.  Selection is a conservative float32 threshold test per pair
 // (no false negatives, see `filter_from_threshold`); survivors are re-scored in float64 exactly as
 // the reference does and merged into a per-query retained list that drives the threshold.
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
@@ -60,14 +61,16 @@ constexpr int DENSE_ROWS = 256;     // rows of the first (dense, threshold seedi
 constexpr int FIXED_ROWS = 1024;    // chunk rows of the bounded-memory fallback / rescan passes
 constexpr int QUERY_BATCH = 65536;  // queries per workspace batch
 constexpr int STATE_OVERFLOW = 1;
-constexpr int SORT_BLOCK = 4096;    // rows are length-sorted inside blocks of this many consecutive rows
-constexpr int POST_ROWS = 2048;     // row positions per posting block = f32 accumulators per warp in k_post (8 KB)
+constexpr int SORT_BLOCK = 4096;    // rows are re-ordered (dense pattern, then length) inside blocks of this many consecutive rows
+constexpr int POST_ROWS = 4096;     // row positions per posting block = u16 fixed-point accumulators per warp in k_post (8 KB)
 constexpr int POST_WARPS = 13;      // warps per CTA; two CTAs (26 warps, 213 KB of accumulators) per SM
 constexpr int POST_LIST = 32;       // per warp: rows of the swept block waiting for the full filter
-constexpr int POST_DESC = 64;       // per warp: listed pieces (start inside the block's postings | length << 24, idf32) of the block being walked
-// tuning knobs of k_post, overridable at build time (-DDS_POST_...=n) for A/B builds; defaults = measured best on C3
+constexpr int POST_DESC = 64;       // per warp: listed pieces (start inside the block's postings | length << 24, fixed-point weight) of the block being walked
+constexpr int DENSE_MAX = 32;       // columns kept out of the postings: their presence is a 32-bit pattern per row
+constexpr int DENSE_MIN_SHARE = 128;   // a column is dense only if it sits in at least 1 / 128 of the rows
+// tuning knobs of k_post, overridable at build time (-DDS_POST_...=n) for A/B builds
 #ifndef DS_POST_RUN
-#define DS_POST_RUN 8
+#define DS_POST_RUN 4
 #endif
 #ifndef DS_POST_DEPTH
 #define DS_POST_DEPTH 4
@@ -77,10 +80,11 @@ constexpr int POST_DESC = 64;       // per warp: listed pieces (start inside the
 #endif
 constexpr int POST_RUN = DS_POST_RUN;      // consecutive posting blocks per warp task (the query's columns are loaded once)
 constexpr int POST_DEPTH = DS_POST_DEPTH;  // posting pieces (<= 64 postings each) in flight per warp
-constexpr int POST_GROUPS = POST_ROWS / 128;   // the block sweep takes 128 rows at a time (<= 32 groups: one lane each)
-constexpr int POST_CTAS = POST_ROWS <= 2048 ? 2 : 1;
-typedef std::conditional<POST_ROWS <= 2048, uint16_t, uint32_t>::type post_off_t;   // segment offsets inside a block
-static_assert(SORT_BLOCK % POST_ROWS == 0 && POST_GROUPS <= 32, "posting blocks must tile the sort blocks");
+constexpr int POST_GROUPS = POST_ROWS / 128;   // bars are kept per 128 rows: 32 groups, one lane each
+constexpr int POST_CTAS = 2;
+typedef uint32_t post_off_t;                   // segment offsets inside a block
+typedef uint16_t post_acc_t;                   // fixed-point accumulator
+static_assert(SORT_BLOCK % POST_ROWS == 0 && POST_GROUPS == 32 && POST_ROWS <= 65536, "posting blocks must tile the sort blocks");
 constexpr int MODE_SCORE = 0;       // retained list = best m by (score, row); drives the running threshold
 constexpr int MODE_ROW = 1;         // retained list = the k highest rows with s64 >= a fixed threshold (rescan)
 
@@ -112,6 +116,14 @@ struct Index {
     uint32_t *seg_base = nullptr;
     float *sums_floor = nullptr;    // [n_sub * POST_GROUPS] smallest sums_pos of every group of 128 positions (+inf padded)
     int n_sub = 0;
+    // Dense columns: the up to 32 columns with the highest document frequency (each in >= 1 / 128 of the rows) have no
+    // postings; which of them a row holds is a 32-bit pattern (bit 31 = the commonest column).  Rows are sorted by
+    // pattern inside their sort block, so 128 consecutive positions mostly share one pattern.
+    uint8_t *dense_bit = nullptr;   // [n_vocab + 1] bit of a dense column, 255 = not dense
+    float *dense_w = nullptr;       // [32] w32 of the dense column of every bit (0 where unused)
+    uint32_t *pat_pos = nullptr;    // [n_truth] dense pattern by position
+    uint32_t *group_pat = nullptr;  // [n_sub * POST_GROUPS] OR of the patterns of every group of 128 positions
+    int n_dense = 0;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -166,7 +178,8 @@ __global__ void k_weights(const double *__restrict__ w64, float *__restrict__ w3
 // into `seg`; PASS 1 appends the block-local position to each of its segments (`seg` = running cursors).
 template <int PASS>
 __global__ void k_post_build(const uint16_t *__restrict__ packed, const uint32_t *__restrict__ chunk_ptr, int64_t n_rows,
-                             int n_vocab, uint32_t *__restrict__ seg, uint16_t *__restrict__ post, int *__restrict__ repeated) {
+                             int n_vocab, const uint8_t *__restrict__ dense_bit, uint32_t *__restrict__ seg, uint16_t *__restrict__ post,
+                             int *__restrict__ repeated) {
     int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= n_rows) return;
     const uint16_t *cols = packed + (size_t)chunk_ptr[pos] * CHUNK_COLS;
@@ -176,13 +189,11 @@ __global__ void k_post_build(const uint16_t *__restrict__ packed, const uint32_t
     for (int i = 0; i < n; ++i) {
         const int col = cols[i];
         if (col >= n_vocab) break;   // sentinel padding: ascending, so nothing follows
-        if (PASS == 0) {
-            if (col == prev) atomicOr(repeated, 1);
-            atomicAdd(block_seg + col, 1u);
-        } else {
-            post[atomicAdd(block_seg + col, 1u)] = (uint16_t)(pos % POST_ROWS);
-        }
+        if (PASS == 0 && col == prev) atomicOr(repeated, 1);
         prev = col;
+        if (dense_bit[col] != 255) continue;   // dense columns live in the row patterns, not in the postings
+        if (PASS == 0) atomicAdd(block_seg + col, 1u);
+        else post[atomicAdd(block_seg + col, 1u)] = (uint16_t)(pos % POST_ROWS);
     }
 }
 
@@ -190,11 +201,13 @@ __global__ void k_post_build(const uint16_t *__restrict__ packed, const uint32_t
 // caller's column order (match_maker.py:172-174)
 __global__ void k_row_prepare(const int64_t *__restrict__ row_ptr, const uint16_t *__restrict__ cols,
                               const float *__restrict__ w32, int n_vocab, int64_t n_rows, const int32_t *__restrict__ perm,
+                              const uint32_t *__restrict__ pat_row, uint32_t *__restrict__ pat_pos,
                               uint32_t *__restrict__ n_chunks, float *__restrict__ sums, float *__restrict__ sums_pos,
                               int compute_sums, int *__restrict__ not_monotone) {
     int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= n_rows) return;
     const int64_t r = perm[pos];
+    pat_pos[pos] = pat_row[r];
     int64_t p0 = row_ptr[r], p1 = row_ptr[r + 1];
     n_chunks[pos] = (uint32_t)((p1 - p0 + CHUNK_COLS - 1) / CHUNK_COLS);
     float acc = 0.0f;
@@ -234,25 +247,63 @@ __global__ void k_row_pack(const int64_t *__restrict__ row_ptr, const uint16_t *
     }
 }
 
-// smallest row sum of every group of 128 consecutive positions (one warp per group)
-__global__ void k_sums_floor(const float *__restrict__ sums_pos, int64_t n_rows, int64_t n_groups, float *__restrict__ out) {
+// smallest row sum and OR of the dense patterns of every group of 128 consecutive positions (one warp per group)
+__global__ void k_sums_floor(const float *__restrict__ sums_pos, const uint32_t *__restrict__ pat_pos, int64_t n_rows, int64_t n_groups,
+                             float *__restrict__ out, uint32_t *__restrict__ out_pat) {
     int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
     int lane = threadIdx.x & 31;
     if (group >= n_groups) return;
     float low = __int_as_float(0x7f800000);
+    uint32_t pat = 0;
     for (int i = lane; i < 128; i += 32) {
         int64_t pos = group * 128 + i;
-        if (pos < n_rows) low = fminf(low, sums_pos[pos]);
+        if (pos < n_rows) {
+            low = fminf(low, sums_pos[pos]);
+            pat |= pat_pos[pos];
+        }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) low = fminf(low, __shfl_xor_sync(0xffffffffu, low, d));
-    if (lane == 0) out[group] = low;
+    pat = __reduce_or_sync(0xffffffffu, pat);
+    if (lane == 0) {
+        out[group] = low;
+        out_pat[group] = pat;
+    }
+}
+
+// document frequency of every column over the rows of this index (rows hold a column once: checked by k_post_build)
+__global__ void k_col_df(const uint16_t *__restrict__ cols, int64_t nnz, int n_vocab, uint32_t *__restrict__ df) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nnz && cols[i] < n_vocab) atomicAdd(df + cols[i], 1u);
+}
+
+// Per original row: its dense pattern and the key its position inside the sort block is sorted by:
+// (sort block, pattern, chunk count) - the top field keeps every block of SORT_BLOCK rows in place.
+__global__ void k_row_keys(const int64_t *__restrict__ row_ptr, const uint16_t *__restrict__ cols, int n_vocab, int64_t n_rows,
+                           const uint8_t *__restrict__ dense_bit, uint32_t *__restrict__ pat_row, unsigned long long *__restrict__ keys,
+                           int32_t *__restrict__ ids) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const int64_t p0 = row_ptr[r], p1 = row_ptr[r + 1];
+    uint32_t pat = 0;
+    if (dense_bit != nullptr) {
+        for (int64_t p = p0; p < p1; ++p) {
+            const int bit = dense_bit[min((int)cols[p], n_vocab)];
+            if (bit != 255) pat |= 1u << bit;
+        }
+    }
+    pat_row[r] = pat;
+    const unsigned long long chunks = (unsigned long long)min((long long)((p1 - p0 + CHUNK_COLS - 1) / CHUNK_COLS), 1023ll);
+    keys[r] = ((unsigned long long)(r / SORT_BLOCK) << 42) | ((unsigned long long)pat << 10) | chunks;
+    ids[r] = (int32_t)r;
 }
 
 // Re-orders the postings of every long segment so that 32 consecutive entries fall into 32 different shared-memory
-// banks of k_post's accumulators (bank = row & 31): entries are ranked by (index within their bank, bank).  The rows
-// of a segment are distinct and their additions commute, so the order inside a segment is free.  One warp per segment.
-constexpr int BALANCE_WARPS = 4;
+// banks of k_post's u16 accumulators (bank = (row / 2) & 31): entries are ranked by (index within their bank, bank).
+// The rows of a segment are distinct and their additions commute, so the order inside a segment is free.  One warp
+// per segment.
+constexpr int BALANCE_WARPS = 2;
+__device__ __forceinline__ int post_bank(int row) { return (row >> 1) & 31; }
 __global__ void __launch_bounds__(BALANCE_WARPS * 32) k_post_balance(uint16_t *__restrict__ post, const post_off_t *__restrict__ seg_off,
                                                                      const uint32_t *__restrict__ seg_base, int64_t n_segments, int n_vocab) {
     __shared__ uint16_t s_rows[BALANCE_WARPS][POST_ROWS];
@@ -270,10 +321,10 @@ __global__ void __launch_bounds__(BALANCE_WARPS * 32) k_post_balance(uint16_t *_
     s_count[warp][lane] = 0;
     for (int i = lane; i < n; i += 32) s_rows[warp][i] = entries[i];
     __syncwarp();
-    for (int i = lane; i < n; i += 32) s_rank[warp][i] = (uint16_t)atomicAdd(&s_count[warp][s_rows[warp][i] & 31], 1);
+    for (int i = lane; i < n; i += 32) s_rank[warp][i] = (uint16_t)atomicAdd(&s_count[warp][post_bank(s_rows[warp][i])], 1);
     __syncwarp();
     for (int i = lane; i < n; i += 32) {
-        const int row = s_rows[warp][i], bank = row & 31, k = s_rank[warp][i];
+        const int row = s_rows[warp][i], bank = post_bank(row), k = s_rank[warp][i];
         int at = 0;
 #pragma unroll
         for (int b = 0; b < 32; ++b) {
@@ -284,7 +335,7 @@ __global__ void __launch_bounds__(BALANCE_WARPS * 32) k_post_balance(uint16_t *_
     }
 }
 
-// 32-bit segment starts -> per block base + 16-bit offsets (half the table k_post has to keep in L2)
+// global segment starts -> per block base + offsets inside the block
 __global__ void k_post_offsets(const uint32_t *__restrict__ seg_start, int n_sub, int n_vocab, post_off_t *__restrict__ seg_off,
                                uint32_t *__restrict__ seg_base, int *__restrict__ too_long) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -292,7 +343,7 @@ __global__ void k_post_offsets(const uint32_t *__restrict__ seg_start, int n_sub
     const int s = (int)(i / (n_vocab + 1)), c = (int)(i % (n_vocab + 1));
     const uint32_t base = seg_start[(size_t)s * n_vocab];
     const uint32_t off = seg_start[(size_t)s * n_vocab + c] - base;   // c == n_vocab: the start of the next block
-    if (sizeof(post_off_t) == 2 && off > 65535u) atomicOr(too_long, 1);
+    if (off >= (1u << 24)) atomicOr(too_long, 1);   // piece descriptors keep starts in 24 bits
     seg_off[i] = (post_off_t)off;
     if (c == 0) seg_base[s] = base;
 }
@@ -516,24 +567,37 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) k_scan(ScanParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K1 posting kernel: the same scores and the same candidates as k_scan's filter pass, from the inverted
-// rows.  One warp task = one query x a run of consecutive blocks of POST_ROWS row positions.  Per block:
-// an f32 accumulator per position in shared memory; the query's columns are walked in ASCENDING id order
-// and every posting of a column adds idf32 to its row - per (query, row) pair that is the reference's
-// float32 accumulation order (match_maker.py:33-47), but only the ~2 % of the (row, column) incidences
-// that hit the query are touched instead of every column of every row.  A row appears once per segment,
-// so the lanes of a piece never collide; __syncwarp() orders consecutive pieces.  Postings are requested
-// POST_DEPTH pieces ahead of their use, the next block's segment bounds one block ahead.
-// After the last column the block is swept (and zeroed): with weights and row sums >= 0, k_scan's filter
-// `sc > fmaf(a, sums, b)` implies sc > b, so only rows above b are listed for the full test.
+// K1 posting kernel: the candidates of k_scan's filter pass (a superset of them, never fewer) from the inverted
+// rows.  One warp task = one query x a run of consecutive blocks of POST_ROWS row positions.
+//
+// A query's columns are split in two.  DENSE columns (the <= 32 commonest trigrams of the index: 3/4 of all
+// (row, column) incidences a query touches) are never walked: which of them a row holds is a 32-bit pattern, rows
+// are sorted by pattern, and the weight a group of 128 rows can gain from them is the sum over (group's OR-ed
+// pattern & query mask).  SPARSE columns are walked through their posting segments: every posting adds the
+// column's weight to its row's accumulator in shared memory.  A row appears once per segment, so the lanes of a
+// piece never collide; __syncwarp() orders consecutive pieces.  Postings are requested POST_DEPTH pieces ahead of
+// their use, the next block's segment bounds one block ahead.
+//
+// Nothing here has to be exact, only conservative: every row that survives is re-scored by k_select in the
+// reference's own float32 order (ascending column ids over the row's resident chunks, match_maker.py:33-47).
+// So the accumulators are 16-bit fixed point (weights rounded UP to 1/S units, S chosen per query so that the
+// largest possible sum fits 65,535): 8 KB per warp hold 4,096 rows, and the sweep that finds the rows above their
+// bar and clears the block reads 8 rows per lane and 128-bit load with two packed-u16 maxima.
+// `post_test` is the one conservative test (monotone in every argument); a group's bar is the largest accumulator
+// value that fails it with the group's smallest row sum and largest dense gain.
 // ---------------------------------------------------------------------------------------------------
 struct PostParams {
     const uint16_t *post;
     const post_off_t *seg_off;
     const uint32_t *seg_base;
     int n_vocab;
+    int64_t n_truth;
     const float *sums;          // by position
     const float *sums_floor;    // [blocks * POST_GROUPS] smallest row sum of every group of 128 positions
+    const uint32_t *group_pat;  // [blocks * POST_GROUPS] OR of the dense patterns of the group
+    const uint32_t *pat_pos;    // [n_truth] dense pattern by position
+    const uint8_t *dense_bit;   // [n_vocab + 1]
+    const float *dense_w;       // [32]
     const float *w32;
     const uint16_t *q_sorted;
     const int64_t *q_ptr;
@@ -551,23 +615,60 @@ struct PostParams {
 
 struct PostPiece {
     uint32_t r0, r1;   // block-local rows of this lane's postings (entries lane and lane + 32 of the piece)
-    float w;
+    uint32_t w;        // fixed-point weight
     int n;             // postings in the piece (warp uniform); 0 = the stream has ended
 };
 
-// full filter for the listed rows of a swept block (kept out of line: the sweep loop stays small)
-__device__ __noinline__ void post_flush(float *acc, const uint16_t *list, int n_list, int base_pos, float2 ab,
-                                        const float *__restrict__ sums, int *cand_count, uint2 *cand, int cap, int b) {
+// per query constants of the conservative test
+struct PostQuery {
+    float2 ab;         // k_scan's filter constants
+    float inv_scale;   // >= 1 / S (0 when the query has no sparse column)
+    float grow;        // 1 + e: covers every float32 rounding between the reference's sum and this bound
+    uint32_t mask;     // the query's dense columns
+};
+
+// float32 sum of the dense weights selected by `bits`, lowest bit first: monotone in `bits` (a superset never sums lower)
+__device__ __forceinline__ float dense_gain(uint32_t bits, const float *s_dense_w) {
+    float v = 0.0f;
+    while (bits != 0) {
+        const int bit = __ffs(bits) - 1;
+        bits &= bits - 1;
+        v = __fadd_rn(v, s_dense_w[bit]);
+    }
+    return v;
+}
+
+// Can a row with fixed-point sparse sum `acc`, dense gain `gain` and filter bar `bar` = fmaf(a, sums, b) reach the
+// threshold?  acc * inv_scale >= the real sparse sum, gain >= the real dense sum up to float32 rounding, and `grow`
+// covers those roundings and the reference's own: the reference's float32 score sum is <= the left-hand side, so
+// k_scan's filter `sc > bar` implies this test.  Monotone: non-decreasing in acc and gain, non-increasing in bar.
+__device__ __forceinline__ bool post_test(int acc, float gain, float bar, const PostQuery &q) {
+    const float upper = __fmul_ru(__fadd_ru(__fmul_ru((float)acc, q.inv_scale), gain), q.grow);
+    return upper > bar;
+}
+
+// full test for the listed rows of a swept block (kept out of line: the sweep loop stays small)
+__device__ __noinline__ void post_flush(post_acc_t *acc, const uint16_t *list, int n_list, int64_t base_pos, float2 ab, float inv_scale,
+                                        float grow, uint32_t mask, int64_t n_truth, const uint32_t *__restrict__ pat_pos,
+                                        const float *__restrict__ sums, int *cand_count, uint2 *cand, int cap,
+                                        const float *s_dense_w, int b) {
     const int lane = threadIdx.x & 31;
+    PostQuery q;
+    q.ab = ab;
+    q.inv_scale = inv_scale;
+    q.grow = grow;
+    q.mask = mask;
     __syncwarp();
     for (int i = lane; i < n_list; i += 32) {
         const int r = list[i];
-        const float sc = acc[r];
-        acc[r] = 0.0f;
-        const int pos = base_pos + r;
-        if (sc > fmaf(ab.x, sums[pos], ab.y)) {
+        const int value = acc[r];
+        acc[r] = 0;
+        const int64_t pos = base_pos + r;
+        if (pos >= n_truth) continue;   // padding of the last block (listed only when a bar is negative)
+        const float gain = dense_gain(__ldg(pat_pos + pos) & q.mask, s_dense_w);
+        if (post_test(value, gain, fmaf(q.ab.x, __ldg(sums + pos), q.ab.y), q)) {
             const int at = atomicAdd(cand_count + b, 1);
-            if (at < cap) cand[(size_t)b * cap + at] = make_uint2((uint32_t)pos, __float_as_uint(sc));
+            if (at < cap) cand[(size_t)b * cap + at] = make_uint2((uint32_t)pos, (uint32_t)value);
         }
     }
     __syncwarp();
@@ -576,20 +677,23 @@ __device__ __noinline__ void post_flush(float *acc, const uint16_t *list, int n_
 __global__ void __launch_bounds__(POST_WARPS * 32, POST_CTAS) k_post(PostParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_next;
+    __shared__ float s_dense_w[DENSE_MAX];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *acc = reinterpret_cast<float *>(smem) + (size_t)warp * POST_ROWS;
-    float4 *acc4 = reinterpret_cast<float4 *>(acc);
-    uint16_t *list = reinterpret_cast<uint16_t *>(smem + (size_t)POST_WARPS * POST_ROWS * 4) + warp * POST_LIST;
-    uint2 *desc = reinterpret_cast<uint2 *>(smem + (size_t)POST_WARPS * (POST_ROWS * 4 + POST_LIST * 2)) + warp * POST_DESC;
+    post_acc_t *acc = reinterpret_cast<post_acc_t *>(smem) + (size_t)warp * POST_ROWS;
+    uint4 *acc4 = reinterpret_cast<uint4 *>(acc);
+    uint16_t *list = reinterpret_cast<uint16_t *>(smem + (size_t)POST_WARPS * POST_ROWS * sizeof(post_acc_t)) + warp * POST_LIST;
+    uint2 *desc = reinterpret_cast<uint2 *>(smem + (size_t)POST_WARPS * (POST_ROWS * sizeof(post_acc_t) + POST_LIST * 2)) + warp * POST_DESC;
     if (threadIdx.x == 0) s_next = 0;
+    if (threadIdx.x < DENSE_MAX) s_dense_w[threadIdx.x] = p.dense_w[threadIdx.x];
     __syncthreads();
     const long long cta_first = (long long)blockIdx.x * p.tasks_per_cta;
     const int cta_tasks = (int)min((long long)p.tasks_per_cta, p.n_tasks - cta_first);
     const unsigned lanes_below = (1u << lane) - 1u;
     const int stride = p.n_vocab + 1;
-    const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    constexpr int SWEEPS = POST_ROWS / 256;   // the sweep takes 256 rows (8 per lane) at a time
 #pragma unroll
-    for (int i = 0; i < POST_GROUPS; ++i) acc4[i * 32 + lane] = zero4;   // every sweep leaves the block zeroed again
+    for (int i = 0; i < SWEEPS; ++i) acc4[i * 32 + lane] = zero4;   // every sweep leaves the block zeroed again
     __syncwarp();
 
     for (;;) {
@@ -600,48 +704,101 @@ __global__ void __launch_bounds__(POST_WARPS * 32, POST_CTAS) k_post(PostParams 
         const long long task = cta_first + local;
         const int run = (int)(task / p.n_batch);
         const int b = (int)(task % p.n_batch);
-        const float2 ab = p.ab[b];
-        if (!(ab.y < __int_as_float(0x7f800000))) continue;   // overflowed / dense-only query: nothing can pass
+        PostQuery pq;
+        pq.ab = p.ab[b];
+        if (!(pq.ab.y < __int_as_float(0x7f800000))) continue;   // overflowed / dense-only query: nothing can pass
         const int s_begin = p.s0 + run * p.run_len;
         const int s_end = min(p.s1, s_begin + p.run_len);
         const int q = p.batch_q[b];
         const int64_t q0 = p.q_ptr[q];
         const int g = (int)(p.q_ptr[q + 1] - q0);
 
-        // up to 32 columns stay in registers for the whole run: lane = column
+        // one pass over the query's columns: dense mask, the sum of the sparse weights (rounded up) -> the scale.
+        // Up to 32 columns stay in registers for the whole run: lane = column.
         const bool cached = g <= 32;
         int col = p.n_vocab;
         float col_w = 0.0f;
-        uint32_t next_beg = 0, next_end = 0;
-        if (cached && lane < g) col = p.q_sorted[q0 + lane];
-        if (col < p.n_vocab) {
-            col_w = __ldg(p.w32 + col);
+        bool col_sparse = false;
+        float sparse_sum = 0.0f;
+        pq.mask = 0;
+        for (int g0 = 0; g0 < g; g0 += 32) {
+            int c = p.n_vocab;
+            if (g0 + lane < g) c = p.q_sorted[q0 + g0 + lane];
+            float w = 0.0f;
+            bool sparse = false;
+            if (c < p.n_vocab) {
+                w = __ldg(p.w32 + c);
+                const int bit = __ldg(p.dense_bit + c);
+                if (bit != 255) pq.mask |= 1u << bit;
+                else sparse = true;
+            }
+            if (sparse) sparse_sum = __fadd_ru(sparse_sum, w);
+            if (cached) {
+                col = c;
+                col_w = w;
+                col_sparse = sparse;
+            }
+        }
+        pq.mask = __reduce_or_sync(0xffffffffu, pq.mask);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) sparse_sum = __fadd_ru(sparse_sum, __shfl_xor_sync(0xffffffffu, sparse_sum, d));
+        // S * (sum of the real sparse weights) + 2 g <= 65,531: no accumulator can overflow (a row holds a column once,
+        // every weight is rounded up by less than two units)
+        float scale = 0.0f;
+        pq.inv_scale = 0.0f;
+        if (sparse_sum > 0.0f && sparse_sum < __int_as_float(0x7f800000)) {
+            scale = __fdiv_rd((float)(65535 - 4 - 2 * min(g, 16000)), sparse_sum);
+            pq.inv_scale = __frcp_ru(scale);
+        }
+        pq.grow = __fadd_ru(1.0f, __fmul_ru((float)(2 * g + 64), 5.9604645e-8f));   // 1 + (2 g + 64) * 2^-24
+        uint32_t col_fix = 0;
+        post_off_t next_beg = 0, next_end = 0;
+        if (col_sparse) {
+            col_fix = min(65535u, __float2uint_ru(__fmul_ru(col_w, scale)));
             const post_off_t *o = p.seg_off + (size_t)s_begin * stride + col;
             next_beg = __ldg(o);
             next_end = __ldg(o + 1);
         }
         uint32_t next_base = __ldg(p.seg_base + s_begin);
-        // lane i (mod POST_GROUPS): the smallest row sum of the block's i-th group of 128 rows
-        float next_floor = __ldg(p.sums_floor + (size_t)s_begin * POST_GROUPS + (lane % POST_GROUPS));
+        // lane i: the smallest row sum and the OR-ed dense pattern of the block's i-th group of 128 rows
+        float next_floor = __ldg(p.sums_floor + (size_t)s_begin * POST_GROUPS + lane);
+        uint32_t next_pat = __ldg(p.group_pat + (size_t)s_begin * POST_GROUPS + lane);
         int n_list = 0;
 
         for (int s = s_begin; s < s_end; ++s) {
             const uint32_t base = next_base;
-            // k_scan's filter with the group's smallest row sum: fmaf is monotone in sums (a >= 0), so a row that
-            // passes the filter is above its group's bar
-            const float my_bar = fmaf(ab.x, next_floor, ab.y);
+            // This lane's group bar: the largest accumulator value that still fails the test with the group's smallest
+            // row sum (fmaf is monotone in sums, a >= 0) and its largest dense gain (the OR of its rows' patterns).
+            // A first guess from the real-number form, then corrected against post_test itself (monotone in acc).
+            int my_bar;
+            {
+                const float bar_f = fmaf(pq.ab.x, next_floor, pq.ab.y);
+                const float gain = dense_gain(next_pat & pq.mask, s_dense_w);
+                // acc * inv_scale + gain > bar / grow, with 1 / grow ~ 2 - grow; NaN (padded group: 0 * inf) compares false
+                const float room = __fmul_rd(__fsub_rd(__fmul_rd(bar_f, __fsub_rd(2.0f, pq.grow)), gain), scale);
+                int guess = room >= 65534.0f ? 65534 : (room >= 1.0f ? (int)room - 1 : -1);
+                if (!(bar_f == bar_f)) guess = 65535;
+                if (pq.inv_scale == 0.0f) guess = post_test(0, gain, bar_f, pq) ? -1 : 65535;   // no sparse column: acc stays 0
+                if (guess < 0 && !post_test(0, gain, bar_f, pq)) guess = 0;
+                if (guess >= 0 && guess < 65535) {
+                    for (int it = 0; it < 64 && guess < 65535 && !post_test(guess + 1, gain, bar_f, pq); ++it) ++guess;
+                    for (int it = 0; it < 64 && guess >= 0 && post_test(guess, gain, bar_f, pq); ++it) --guess;
+                    if (guess >= 0 && post_test(guess, gain, bar_f, pq)) guess = -1;   // still passing: list the whole group
+                }
+                my_bar = guess;
+            }
             if (s + 1 < s_end) {
                 next_base = __ldg(p.seg_base + s + 1);
-                next_floor = __ldg(p.sums_floor + (size_t)(s + 1) * POST_GROUPS + (lane % POST_GROUPS));
+                next_floor = __ldg(p.sums_floor + (size_t)(s + 1) * POST_GROUPS + lane);
+                next_pat = __ldg(p.group_pat + (size_t)(s + 1) * POST_GROUPS + lane);
             }
             for (int g0 = 0; g0 < g; g0 += 32) {
-                uint32_t my_beg = 0, my_end = 0;
-                float my_w = 0.0f;
+                uint32_t my_beg = 0, my_end = 0, my_w = 0;
                 if (cached) {
                     my_beg = next_beg;
                     my_end = next_end;
-                    my_w = col_w;
-                    if (s + 1 < s_end && col < p.n_vocab) {
+                    my_w = col_fix;
+                    if (s + 1 < s_end && col_sparse) {
                         const post_off_t *o = p.seg_off + (size_t)(s + 1) * stride + col;
                         next_beg = __ldg(o);
                         next_end = __ldg(o + 1);
@@ -649,39 +806,49 @@ __global__ void __launch_bounds__(POST_WARPS * 32, POST_CTAS) k_post(PostParams 
                 } else {
                     int c = p.n_vocab;
                     if (g0 + lane < g) c = p.q_sorted[q0 + g0 + lane];
-                    if (c < p.n_vocab) {
+                    if (c < p.n_vocab && __ldg(p.dense_bit + c) == 255) {
                         const post_off_t *o = p.seg_off + (size_t)s * stride + c;
                         my_beg = __ldg(o);
                         my_end = __ldg(o + 1);
-                        my_w = __ldg(p.w32 + c);
+                        my_w = min(65535u, __float2uint_ru(__fmul_ru(__ldg(p.w32 + c), scale)));
                     }
                 }
-                // The non-empty segments are cut into pieces of <= 64 postings, listed in shared memory in ascending
-                // column order (lane = column: a prefix sum of the piece counts gives every lane its slots); the walk
-                // then is a plain counted loop over the list.  Lists longer than POST_DESC pieces go in rounds.
+                // The non-empty segments are cut into pieces of <= 64 postings, listed in shared memory (lane = column:
+                // a prefix sum of the piece counts gives every lane its slots); the walk then is a plain counted loop
+                // over the list.  Lists longer than POST_DESC pieces go in rounds.
                 const uint32_t n_mine = my_end > my_beg ? my_end - my_beg : 0u;
                 unsigned remaining = __ballot_sync(0xffffffffu, n_mine != 0);
                 const uint16_t *lane_post = p.post + base + lane;   // piece starts are kept relative to the block
+                uint32_t done = 0;                                   // postings of this lane's segment already listed
                 while (remaining != 0) {
                     const bool mine = (remaining >> lane) & 1u;
-                    const uint32_t pieces = mine ? (n_mine + 63u) >> 6 : 0u;
+                    const uint32_t left_mine = n_mine - done;
+                    const uint32_t pieces = mine ? (left_mine + 63u) >> 6 : 0u;
                     uint32_t incl = pieces;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
                         const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
                         if (lane >= d) incl += v;
                     }
+                    // lanes whose pieces all fit go in this round; the first lane that does not fit lists what fits of
+                    // its segment (a segment of a 4,096-row block can alone hold more than POST_DESC pieces)
+                    const uint32_t before = incl - pieces;
                     const bool fits = mine && incl <= (uint32_t)POST_DESC;
-                    const unsigned fit_mask = __ballot_sync(0xffffffffu, fits);   // a prefix of `remaining`: at least its first lane
-                    const int n_pieces = (int)__shfl_sync(0xffffffffu, incl, 31 - __clz(fit_mask));
-                    if (fits) {
-                        uint32_t at = incl - pieces, start = my_beg, left = n_mine;
-                        for (uint32_t t = 0; t < pieces; ++t) {
-                            desc[at] = make_uint2(start | (min(left, 64u) << 24), __float_as_uint(my_w));   // start < 2^24: a block's postings
+                    const bool partial = mine && !fits && before < (uint32_t)POST_DESC;
+                    const uint32_t take = fits ? pieces : (partial ? (uint32_t)POST_DESC - before : 0u);
+                    const unsigned fit_mask = __ballot_sync(0xffffffffu, fits);
+                    const unsigned part_mask = __ballot_sync(0xffffffffu, partial);
+                    const int last_lane = 31 - __clz(fit_mask | part_mask);   // the masks are not both empty: the first remaining lane takes >= 1
+                    const int n_pieces = (int)__shfl_sync(0xffffffffu, before + take, last_lane);
+                    if (take != 0) {
+                        uint32_t at = before, start = my_beg + done, left = left_mine;
+                        for (uint32_t t = 0; t < take; ++t) {
+                            desc[at] = make_uint2(start | (min(left, 64u) << 24), my_w);   // start < 2^24: checked at build time
                             ++at;
                             start += 64u;
-                            left -= 64u;
+                            left -= min(left, 64u);
                         }
+                        if (partial) done += take * 64u;
                     }
                     remaining &= ~fit_mask;
                     __syncwarp();
@@ -692,7 +859,7 @@ __global__ void __launch_bounds__(POST_WARPS * 32, POST_CTAS) k_post(PostParams 
                         const uint2 d = desc[index];
                         const int n = (int)(d.x >> 24);
                         piece.n = n;
-                        piece.w = __uint_as_float(d.y);
+                        piece.w = d.y;
                         const uint16_t *src = lane_post + (d.x & 0xffffffu);
                         if (lane < n) piece.r0 = __ldg(src);
                         if (lane + 32 < n) piece.r1 = __ldg(src + 32);
@@ -703,7 +870,7 @@ __global__ void __launch_bounds__(POST_WARPS * 32, POST_CTAS) k_post(PostParams 
                         ring[d].r0 = 0;
                         ring[d].r1 = 0;
                         ring[d].n = 0;
-                        ring[d].w = 0.0f;
+                        ring[d].w = 0;
                         if (d < n_pieces) fetch(d, ring[d]);
                     }
                     for (int first_piece = 0; first_piece < n_pieces; first_piece += POST_DEPTH) {
@@ -712,51 +879,63 @@ __global__ void __launch_bounds__(POST_WARPS * 32, POST_CTAS) k_post(PostParams 
                             const int index = first_piece + d;
                             if (index >= n_pieces) break;
                             const int n = ring[d].n;
-                            const float add = ring[d].w;
-                            float *slot0 = acc + ring[d].r0, *slot1 = acc + ring[d].r1;
+                            const uint32_t add = ring[d].w;
+                            post_acc_t *slot0 = acc + ring[d].r0, *slot1 = acc + ring[d].r1;
                             const bool first = lane < n, second = lane + 32 < n;
-                            float a0 = 0.0f, a1 = 0.0f;
+                            uint32_t a0 = 0, a1 = 0;
                             if (first) a0 = *slot0;
                             if (second) a1 = *slot1;
                             if (index + POST_DEPTH < n_pieces) fetch(index + POST_DEPTH, ring[d]);
-                            if (first) *slot0 = __fadd_rn(a0, add);
-                            if (second) *slot1 = __fadd_rn(a1, add);
-                            __syncwarp();   // the next piece may belong to the next column and touch the same rows
+                            if (first) *slot0 = (post_acc_t)(a0 + add);
+                            if (second) *slot1 = (post_acc_t)(a1 + add);
+                            __syncwarp();   // the next piece may belong to another column and touch the same rows
                         }
                     }
                     __syncwarp();   // the list is rewritten by the next round
                 }
             }
 
-            // sweep and zero the block, 128 rows (4 per lane) at a time; rows above their group's bar wait in `list`
-            // (their accumulators stay) for the full filter
-            const int base_pos = s * POST_ROWS;
+            // sweep and zero the block, 256 rows (8 per lane, one 128-bit load) at a time; rows above their group's bar
+            // wait in `list` (their accumulators stay) for the full test
+            const int64_t base_pos = (int64_t)s * POST_ROWS;
 #pragma unroll 2
-            for (int i = 0; i < POST_GROUPS; ++i) {
+            for (int i = 0; i < SWEEPS; ++i) {
                 const int idx = i * 32 + lane;
-                const float bar = __shfl_sync(0xffffffffu, my_bar, i);
-                const float4 v = acc4[idx];
-                const bool hit = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) > bar;
+                const int bar = __shfl_sync(0xffffffffu, my_bar, 2 * i + (lane >> 4));   // lanes 0-15 / 16-31: two groups
+                const uint4 v = acc4[idx];
+                unsigned m = __vimax3_u16x2(v.x, v.y, v.z);
+                m = __vmaxu2(m, v.w);
+                const bool hit = (int)max(m & 0xffffu, m >> 16) > bar;
                 if (__ballot_sync(0xffffffffu, hit) == 0) {
                     acc4[idx] = zero4;
                     continue;
                 }
-                const float vals[4] = {v.x, v.y, v.z, v.w};
-                acc4[idx] = make_float4(v.x > bar ? v.x : 0.0f, v.y > bar ? v.y : 0.0f, v.z > bar ? v.z : 0.0f, v.w > bar ? v.w : 0.0f);
+                const uint32_t words[4] = {v.x, v.y, v.z, v.w};
+                uint32_t kept[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const bool above = vals[c] > bar;
+                    const uint32_t lo = words[c] & 0xffffu, hi = words[c] >> 16;
+                    kept[c] = ((int)lo > bar ? lo : 0u) | ((int)hi > bar ? (hi << 16) : 0u);
+                }
+                acc4[idx] = make_uint4(kept[0], kept[1], kept[2], kept[3]);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int value = (int)((words[c >> 1] >> ((c & 1) * 16)) & 0xffffu);
+                    const bool above = value > bar;
                     const unsigned above_mask = __ballot_sync(0xffffffffu, above);
+                    if (above_mask == 0) continue;
                     if (n_list + __popc(above_mask) > POST_LIST) {
-                        post_flush(acc, list, n_list, base_pos, ab, p.sums, p.cand_count, p.cand, p.cap, b);
+                        post_flush(acc, list, n_list, base_pos, pq.ab, pq.inv_scale, pq.grow, pq.mask, p.n_truth, p.pat_pos, p.sums, p.cand_count, p.cand,
+                                   p.cap, s_dense_w, b);
                         n_list = 0;
                     }
-                    if (above) list[n_list + __popc(above_mask & lanes_below)] = (uint16_t)(idx * 4 + c);
+                    if (above) list[n_list + __popc(above_mask & lanes_below)] = (uint16_t)(idx * 8 + c);
                     n_list += __popc(above_mask);
                 }
             }
             if (n_list > 0) {
-                post_flush(acc, list, n_list, base_pos, ab, p.sums, p.cand_count, p.cand, p.cap, b);
+                post_flush(acc, list, n_list, base_pos, pq.ab, pq.inv_scale, pq.grow, pq.mask, p.n_truth, p.pat_pos, p.sums, p.cand_count, p.cand,
+                                   p.cap, s_dense_w, b);
                 n_list = 0;
             }
             __syncwarp();
@@ -790,7 +969,36 @@ struct SelectParams {
     int *state;
     int *overflow_count;
     int max_items;      // smem capacity per warp
+    // candidates of k_post carry no score: it is computed here, in the reference's own float32 order
+    int rescore;
+    const chunk_t *chunks;
+    const uint32_t *chunk_ptr;
+    const float *w32;
+    int n_vocab;
+    const uint16_t *q_sorted;
+    const int64_t *q_ptr;
 };
+
+// fast_jaccard's float32 sum for one (query, row) pair (match_maker.py:33-47): idf32 of the shared columns added in
+// ascending column id order - a merge of the query's ascending columns with the row's ascending chunks
+__device__ __forceinline__ float exact_intersection(const uint16_t *__restrict__ q_cols, int g, const chunk_t *__restrict__ chunks, uint32_t c0,
+                                                    uint32_t c1, const float *__restrict__ w32, int n_vocab) {
+    float sc = 0.0f;
+    int i = 0;
+    for (uint32_t c = c0; c < c1 && i < g; ++c) {
+        const chunk_t ch = __ldg(chunks + c);
+        const uint32_t words[CHUNK_COLS / 2] = {ch.x, ch.y};
+#pragma unroll
+        for (int k = 0; k < CHUNK_COLS; ++k) {
+            const int rc = (int)((words[k >> 1] >> ((k & 1) * 16)) & 0xffffu);
+            if (rc >= n_vocab) break;   // sentinel padding
+            while (i < g && (int)q_cols[i] < rc) ++i;
+            if (i < g && (int)q_cols[i] == rc) sc = __fadd_rn(sc, __ldg(w32 + rc));
+        }
+    }
+    return sc;
+}
+
 
 __global__ void __launch_bounds__(128) k_select(SelectParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -852,7 +1060,13 @@ __global__ void __launch_bounds__(128) k_select(SelectParams p) {
             int row = 0;
             if (i < cnt) {
                 uint2 c = p.cand[(size_t)b * p.cap + i];
-                s = exact_score(__uint_as_float(c.y), p.sums[c.x], mx);
+                float sc = __uint_as_float(c.y);
+                if (p.rescore) {
+                    const int64_t q0 = p.q_ptr[q];
+                    sc = exact_intersection(p.q_sorted + q0, (int)(p.q_ptr[q + 1] - q0), p.chunks, p.chunk_ptr[c.x], p.chunk_ptr[c.x + 1],
+                                            p.w32, p.n_vocab);
+                }
+                s = exact_score(sc, p.sums[c.x], mx);
                 row = p.perm[c.x];
                 pass = s > 0.0 && s >= theta;
             }
@@ -1250,8 +1464,13 @@ static int launch_post(const Index &ix, cudaStream_t stream, PostParams pp, int 
     pp.seg_off = ix.seg_off;
     pp.seg_base = ix.seg_base;
     pp.n_vocab = ix.n_vocab;
+    pp.n_truth = ix.n_truth;
     pp.sums = ix.sums_pos;
     pp.sums_floor = ix.sums_floor;
+    pp.group_pat = ix.group_pat;
+    pp.pat_pos = ix.pat_pos;
+    pp.dense_bit = ix.dense_bit;
+    pp.dense_w = ix.dense_w;
     pp.w32 = ix.w32;
     pp.s0 = s0;
     pp.s1 = s1;
@@ -1263,7 +1482,7 @@ static int launch_post(const Index &ix, cudaStream_t stream, PostParams pp, int 
     pp.tasks_per_cta = (int)std::min<long long>(POST_WARPS * DS_POST_TASKS, std::max<long long>(POST_WARPS, ceil_div(pp.n_tasks, (long long)148 * 2 * 2)));
     const long long ctas = ceil_div(pp.n_tasks, (long long)pp.tasks_per_cta);
     if (ctas > INT32_MAX) return fail(DS_ERR_UNSUPPORTED, "too many posting tasks in one launch");
-    const size_t smem = (size_t)POST_WARPS * (POST_ROWS * 4 + POST_LIST * 2 + POST_DESC * 8);
+    const size_t smem = (size_t)POST_WARPS * (POST_ROWS * sizeof(post_acc_t) + POST_LIST * 2 + POST_DESC * 8);
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     if (g_profile.enabled) {
         DS_CUDA(cudaEventCreate(&ev_start));
@@ -1402,6 +1621,12 @@ static int run_pipeline(Workspace &call_ws, const Index &ix, const QuerySet &qs,
     sel.ab = d_ab;
     sel.state = d_state;
     sel.overflow_count = d_overflow;
+    sel.chunks = ix.chunks;
+    sel.chunk_ptr = ix.chunk_ptr;
+    sel.w32 = ix.w32;
+    sel.n_vocab = ix.n_vocab;
+    sel.q_sorted = qs.d_sorted;
+    sel.q_ptr = qs.d_ptr;
 
     const int64_t n = ix.n_truth;
     int64_t r0 = 0;
@@ -1418,7 +1643,7 @@ static int run_pipeline(Workspace &call_ws, const Index &ix, const QuerySet &qs,
             if (r1 > POST_ROWS) r1 = ceil_div(r1, (int64_t)POST_ROWS) * POST_ROWS;
             r1 = std::min<int64_t>(n, r1);
         }
-        const bool inverted = !dense && ix.post != nullptr && r0 % POST_ROWS == 0 && (r0 >= 2 * POST_ROWS || mode == MODE_ROW);
+        const bool inverted = !dense && ix.post != nullptr && r0 % POST_ROWS == 0 && (r0 >= POST_ROWS || mode == MODE_ROW);
         if (inverted) {
             DS_CHECK(launch_post(ix, stream, pp, (int)(r0 / POST_ROWS), (int)ceil_div(r1, (int64_t)POST_ROWS)));
         } else {
@@ -1430,6 +1655,7 @@ static int run_pipeline(Workspace &call_ws, const Index &ix, const QuerySet &qs,
         sel.dense = dense ? d_dense : nullptr;
         sel.dense_rows = dense ? (int)(r1 - r0) : 0;
         sel.dense_r0 = (int)r0;
+        sel.rescore = inverted ? 1 : 0;
         DS_CHECK(launch_select(stream, sel));
         r0 = r1;
         first = false;
@@ -1642,28 +1868,10 @@ int ds_index_create(ds_index **out, int device, int64_t n_truth, int32_t n_vocab
     }
     const int64_t nnz = h_ptr[(size_t)n_truth];
     if (h_ptr[0] != 0 || nnz < 0) return fail(DS_ERR_BAD_ARG, "t_row_ptr must start at 0 and be non-decreasing");
-    // position -> original row: stable counting sort by chunk count inside blocks of SORT_BLOCK rows
-    std::vector<int32_t> h_perm((size_t)n_truth);
-    {
-        std::vector<int32_t> bucket_start;
-        for (int64_t b0 = 0; b0 < n_truth; b0 += SORT_BLOCK) {
-            const int64_t b1 = std::min<int64_t>(n_truth, b0 + SORT_BLOCK);
-            int64_t max_chunks = 0;
-            for (int64_t r = b0; r < b1; ++r) {
-                const int64_t g = h_ptr[(size_t)r + 1] - h_ptr[(size_t)r];
-                if (g < 0) return fail(DS_ERR_BAD_ARG, "t_row_ptr is decreasing at row %lld", (long long)r);
-                max_chunks = std::max(max_chunks, (g + CHUNK_COLS - 1) / CHUNK_COLS);
-            }
-            bucket_start.assign((size_t)max_chunks + 2, 0);
-            for (int64_t r = b0; r < b1; ++r) bucket_start[(size_t)((h_ptr[(size_t)r + 1] - h_ptr[(size_t)r] + CHUNK_COLS - 1) / CHUNK_COLS) + 1]++;
-            for (size_t c = 1; c < bucket_start.size(); ++c) bucket_start[c] += bucket_start[c - 1];
-            for (int64_t r = b0; r < b1; ++r) {
-                const size_t c = (size_t)((h_ptr[(size_t)r + 1] - h_ptr[(size_t)r] + CHUNK_COLS - 1) / CHUNK_COLS);
-                h_perm[(size_t)(b0 + bucket_start[c]++)] = (int32_t)r;
-            }
-        }
-    }
+    for (int64_t r = 0; r < n_truth; ++r)
+        if (h_ptr[(size_t)r + 1] < h_ptr[(size_t)r]) return fail(DS_ERR_BAD_ARG, "t_row_ptr is decreasing at row %lld", (long long)r);
     if (nnz > 0 && t_col_ids == nullptr) return fail(DS_ERR_BAD_ARG, "t_col_ids is NULL");
+    if (ceil_div(nnz, CHUNK_COLS) + n_truth >= ((int64_t)1 << 32)) return fail(DS_ERR_UNSUPPORTED, "index too large for 32-bit chunk offsets");
 
     ds_index *handle = new (std::nothrow) ds_index();
     if (handle == nullptr) return fail(DS_ERR_NO_MEMORY, "out of host memory");
@@ -1684,27 +1892,85 @@ int ds_index_create(ds_index **out, int device, int64_t n_truth, int32_t n_vocab
         DS_CHECK(ws.stage_in(&d_cols, t_col_ids, (size_t)nnz));
         DS_CHECK(ws.stage_in(&d_w64_in, idf64_by_col, (size_t)n_vocab));
         DS_CHECK(ws.stage_in(&d_sums_in, sums_truth_f32, (size_t)n_truth));
+        const size_t rows_alloc = (size_t)std::max<int64_t>(1, n_truth);
         DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.w64), (size_t)n_vocab * 8, stream));
         DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.w32), ((size_t)n_vocab + 1) * 4, stream));
-        DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.sums), (size_t)std::max<int64_t>(1, n_truth) * 4, stream));
-        DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.sums_pos), (size_t)std::max<int64_t>(1, n_truth) * 4, stream));
-        DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.perm), (size_t)std::max<int64_t>(1, n_truth) * 4, stream));
-        DS_CUDA(cudaMemcpyAsync(ix.perm, h_perm.data(), (size_t)n_truth * 4, cudaMemcpyHostToDevice, stream));
+        DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.sums), rows_alloc * 4, stream));
+        DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.sums_pos), rows_alloc * 4, stream));
+        DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.perm), rows_alloc * 4, stream));
+        DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.pat_pos), rows_alloc * 4, stream));
         DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.chunk_ptr), ((size_t)n_truth + 1) * 4, stream));
+        DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.dense_bit), (size_t)n_vocab + 1, stream));
+        DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.dense_w), DENSE_MAX * 4, stream));
         DS_CUDA(cudaMemcpyAsync(ix.w64, d_w64_in, (size_t)n_vocab * 8, cudaMemcpyDeviceToDevice, stream));
         int *d_post_flags = nullptr;   // [0]: a weight or row sum is negative / NaN, [1]: a row repeats a column, [2]: a block is too long
         DS_CHECK(ws.alloc(&d_post_flags, 3));
         DS_CUDA(cudaMemsetAsync(d_post_flags, 0, 12, stream));
         k_weights<<<(unsigned)ceil_div(n_vocab + 1, 256), 256, 0, stream>>>(ix.w64, ix.w32, n_vocab, d_post_flags);
         DS_LAUNCHED("k_weights");
+
+        // inverted form for k_post wanted?  (small indexes: the dense sweep of the first rows covers them)
+        const int64_t n_sub = ceil_div(n_truth, (int64_t)POST_ROWS);
+        const int64_t n_seg = n_sub * n_vocab;
+        const bool want_post = n_truth > 2 * POST_ROWS && n_seg < ((int64_t)1 << 30) && (uint64_t)(nnz + 4 * n_truth) < ((uint64_t)1 << 32) - 256;
+
+        // dense columns: the (at most 32) commonest columns that sit in >= 1 / 128 of the rows; bit 31 = the commonest
+        std::vector<uint8_t> h_dense_bit((size_t)n_vocab + 1, 255);
+        float h_dense_w[DENSE_MAX] = {0.0f};
+        ix.n_dense = 0;
+        if (want_post && nnz > 0) {
+            uint32_t *d_df = nullptr;
+            DS_CHECK(ws.alloc(&d_df, (size_t)n_vocab));
+            DS_CUDA(cudaMemsetAsync(d_df, 0, (size_t)n_vocab * 4, stream));
+            k_col_df<<<(unsigned)ceil_div(nnz, 256), 256, 0, stream>>>(d_cols, nnz, n_vocab, d_df);
+            DS_LAUNCHED("k_col_df");
+            std::vector<uint32_t> h_df((size_t)n_vocab);
+            std::vector<float> h_w32((size_t)n_vocab);
+            DS_CUDA(cudaMemcpyAsync(h_df.data(), d_df, (size_t)n_vocab * 4, cudaMemcpyDeviceToHost, stream));
+            DS_CUDA(cudaMemcpyAsync(h_w32.data(), ix.w32, (size_t)n_vocab * 4, cudaMemcpyDeviceToHost, stream));
+            DS_CUDA(cudaStreamSynchronize(stream));
+            std::vector<int32_t> order;
+            const uint32_t least = (uint32_t)std::max<int64_t>(1, n_truth / DENSE_MIN_SHARE);
+            for (int32_t c = 0; c < n_vocab; ++c)
+                if (h_df[(size_t)c] >= least && h_w32[(size_t)c] >= 0.0f && std::isfinite(h_w32[(size_t)c])) order.push_back(c);
+            std::sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return h_df[(size_t)x] != h_df[(size_t)y] ? h_df[(size_t)x] > h_df[(size_t)y] : x < y; });
+            if (order.size() > (size_t)DENSE_MAX) order.resize(DENSE_MAX);
+            ix.n_dense = (int)order.size();
+            for (int rank = 0; rank < ix.n_dense; ++rank) {
+                const int bit = DENSE_MAX - 1 - rank;
+                h_dense_bit[(size_t)order[(size_t)rank]] = (uint8_t)bit;
+                h_dense_w[bit] = h_w32[(size_t)order[(size_t)rank]];
+            }
+        }
+        DS_CUDA(cudaMemcpyAsync(ix.dense_bit, h_dense_bit.data(), (size_t)n_vocab + 1, cudaMemcpyHostToDevice, stream));
+        DS_CUDA(cudaMemcpyAsync(ix.dense_w, h_dense_w, DENSE_MAX * 4, cudaMemcpyHostToDevice, stream));
+
+        // position -> original row: inside every block of SORT_BLOCK rows sorted by (dense pattern, chunk count)
+        uint32_t *d_pat_row = nullptr;
+        unsigned long long *d_keys = nullptr, *d_keys_sorted = nullptr;
+        int32_t *d_ids = nullptr;
+        DS_CHECK(ws.alloc(&d_pat_row, rows_alloc));
+        DS_CHECK(ws.alloc(&d_keys, rows_alloc));
+        DS_CHECK(ws.alloc(&d_keys_sorted, rows_alloc));
+        DS_CHECK(ws.alloc(&d_ids, rows_alloc));
         uint32_t *d_counts = nullptr;
         DS_CHECK(ws.alloc(&d_counts, (size_t)n_truth + 1));
         DS_CUDA(cudaMemsetAsync(d_counts, 0, ((size_t)n_truth + 1) * 4, stream));
         if (n_truth > 0) {
+            k_row_keys<<<(unsigned)ceil_div(n_truth, 256), 256, 0, stream>>>(d_ptr, d_cols, n_vocab, n_truth, ix.dense_bit, d_pat_row, d_keys, d_ids);
+            DS_LAUNCHED("k_row_keys");
+            int end_bit = 42;
+            while (end_bit < 64 && ((int64_t)1 << (end_bit - 42)) <= ceil_div(n_truth, (int64_t)SORT_BLOCK)) ++end_bit;
+            size_t sort_bytes = 0;
+            DS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, d_keys, d_keys_sorted, d_ids, ix.perm, (int)n_truth, 0, end_bit, stream));
+            unsigned char *d_sort_temp = nullptr;
+            DS_CHECK(ws.alloc(&d_sort_temp, sort_bytes));
+            DS_CUDA(cub::DeviceRadixSort::SortPairs(d_sort_temp, sort_bytes, d_keys, d_keys_sorted, d_ids, ix.perm, (int)n_truth, 0, end_bit, stream));
+            g_kernel_launches.fetch_add(1);
             if (d_sums_in != nullptr)
                 DS_CUDA(cudaMemcpyAsync(ix.sums, d_sums_in, (size_t)n_truth * 4, cudaMemcpyDeviceToDevice, stream));
-            k_row_prepare<<<(unsigned)ceil_div(n_truth, 256), 256, 0, stream>>>(d_ptr, d_cols, ix.w32, n_vocab, n_truth, ix.perm, d_counts,
-                                                                               ix.sums, ix.sums_pos, d_sums_in == nullptr ? 1 : 0, d_post_flags);
+            k_row_prepare<<<(unsigned)ceil_div(n_truth, 256), 256, 0, stream>>>(d_ptr, d_cols, ix.w32, n_vocab, n_truth, ix.perm, d_pat_row, ix.pat_pos,
+                                                                               d_counts, ix.sums, ix.sums_pos, d_sums_in == nullptr ? 1 : 0, d_post_flags);
             DS_LAUNCHED("k_row_prepare");
         }
         size_t temp_bytes = 0;
@@ -1716,7 +1982,6 @@ int ds_index_create(ds_index **out, int device, int64_t n_truth, int32_t n_vocab
         uint32_t total_chunks = 0;
         DS_CUDA(cudaMemcpyAsync(&total_chunks, ix.chunk_ptr + n_truth, 4, cudaMemcpyDeviceToHost, stream));
         DS_CUDA(cudaStreamSynchronize(stream));
-        if (ceil_div(nnz, CHUNK_COLS) + n_truth >= ((int64_t)1 << 32)) return fail(DS_ERR_UNSUPPORTED, "index too large for 32-bit chunk offsets");
         ix.n_chunks = total_chunks;
         DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.chunks), std::max<size_t>(1, (size_t)total_chunks) * sizeof(chunk_t), stream));
         if (n_truth > 0) {
@@ -1724,10 +1989,7 @@ int ds_index_create(ds_index **out, int device, int64_t n_truth, int32_t n_vocab
                                                                                  (uint16_t)n_vocab, reinterpret_cast<uint16_t *>(ix.chunks));
             DS_LAUNCHED("k_row_pack");
         }
-        // inverted form for k_post (skipped for small indexes: the dense sweep of the first rows covers them)
-        const int64_t n_sub = ceil_div(n_truth, (int64_t)POST_ROWS);
-        const int64_t n_seg = n_sub * n_vocab;
-        if (n_truth > 2 * POST_ROWS && n_seg < ((int64_t)1 << 30) && (uint64_t)total_chunks * CHUNK_COLS < ((uint64_t)1 << 32) - 256) {
+        if (want_post) {
             ix.n_sub = (int)n_sub;
             uint32_t *d_seg_start = nullptr;
             unsigned char *d_seg_temp = nullptr;
@@ -1735,13 +1997,15 @@ int ds_index_create(ds_index **out, int device, int64_t n_truth, int32_t n_vocab
             DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.seg_off), (size_t)n_sub * (n_vocab + 1) * sizeof(post_off_t), stream));
             DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.seg_base), (size_t)n_sub * 4, stream));
             DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.sums_floor), (size_t)n_sub * POST_GROUPS * 4, stream));
-            k_sums_floor<<<(unsigned)ceil_div(n_sub * POST_GROUPS * 32, 256), 256, 0, stream>>>(ix.sums_pos, n_truth, n_sub * POST_GROUPS, ix.sums_floor);
+            DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.group_pat), (size_t)n_sub * POST_GROUPS * 4, stream));
+            k_sums_floor<<<(unsigned)ceil_div(n_sub * POST_GROUPS * 32, 256), 256, 0, stream>>>(ix.sums_pos, ix.pat_pos, n_truth, n_sub * POST_GROUPS,
+                                                                                               ix.sums_floor, ix.group_pat);
             DS_LAUNCHED("k_sums_floor");
             DS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ix.post), std::max<size_t>(1, (size_t)total_chunks * CHUNK_COLS) * 2, stream));
             DS_CUDA(cudaMemsetAsync(d_seg_start, 0, ((size_t)n_seg + 1) * 4, stream));
             const uint16_t *packed = reinterpret_cast<const uint16_t *>(ix.chunks);
-            k_post_build<0><<<(unsigned)ceil_div(n_truth, 256), 256, 0, stream>>>(packed, ix.chunk_ptr, n_truth, n_vocab, d_seg_start, nullptr,
-                                                                                  d_post_flags + 1);
+            k_post_build<0><<<(unsigned)ceil_div(n_truth, 256), 256, 0, stream>>>(packed, ix.chunk_ptr, n_truth, n_vocab, ix.dense_bit, d_seg_start,
+                                                                                  nullptr, d_post_flags + 1);
             DS_LAUNCHED("k_post_build");
             size_t seg_temp_bytes = 0;
             DS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, seg_temp_bytes, d_seg_start, d_seg_start, (int)(n_seg + 1), stream));
@@ -1751,8 +2015,8 @@ int ds_index_create(ds_index **out, int device, int64_t n_truth, int32_t n_vocab
             k_post_offsets<<<(unsigned)ceil_div(n_sub * (n_vocab + 1), 256), 256, 0, stream>>>(d_seg_start, (int)n_sub, n_vocab, ix.seg_off,
                                                                                               ix.seg_base, d_post_flags + 2);
             DS_LAUNCHED("k_post_offsets");
-            k_post_build<1><<<(unsigned)ceil_div(n_truth, 256), 256, 0, stream>>>(packed, ix.chunk_ptr, n_truth, n_vocab, d_seg_start, ix.post,
-                                                                                  d_post_flags + 1);   // d_seg_start = running cursors from here on
+            k_post_build<1><<<(unsigned)ceil_div(n_truth, 256), 256, 0, stream>>>(packed, ix.chunk_ptr, n_truth, n_vocab, ix.dense_bit, d_seg_start,
+                                                                                  ix.post, d_post_flags + 1);   // d_seg_start = running cursors from here on
             DS_LAUNCHED("k_post_build");
             k_post_balance<<<(unsigned)ceil_div(n_seg, BALANCE_WARPS), BALANCE_WARPS * 32, 0, stream>>>(ix.post, ix.seg_off, ix.seg_base, n_seg,
                                                                                                  n_vocab);
@@ -1766,7 +2030,9 @@ int ds_index_create(ds_index **out, int device, int64_t n_truth, int32_t n_vocab
             cudaFreeAsync(ix.seg_off, stream);
             cudaFreeAsync(ix.seg_base, stream);
             cudaFreeAsync(ix.sums_floor, stream);
+            cudaFreeAsync(ix.group_pat, stream);
             ix.sums_floor = nullptr;
+            ix.group_pat = nullptr;
             ix.post = nullptr;
             ix.seg_off = nullptr;
             ix.seg_base = nullptr;
@@ -1788,7 +2054,8 @@ int ds_index_destroy(ds_index *index) {
     // synchronisation, unlike cudaFree.  Freed on the stream of the latest call that used the index, so the
     // pool cannot hand the memory out again while kernels of that call are still in flight.
     void *buffers[] = {index->ix.chunks, index->ix.chunk_ptr, index->ix.sums, index->ix.sums_pos, index->ix.perm, index->ix.w32, index->ix.w64,
-                       index->ix.post, index->ix.seg_off, index->ix.seg_base, index->ix.sums_floor};
+                       index->ix.post, index->ix.seg_off, index->ix.seg_base, index->ix.sums_floor, index->ix.group_pat, index->ix.pat_pos,
+                       index->ix.dense_bit, index->ix.dense_w};
     for (void *b : buffers)
         if (b != nullptr) cudaFreeAsync(b, index->ix.last_stream);
     delete index;
