@@ -61,7 +61,7 @@ constexpr int DENSE_ROWS = 256;     // rows of the first (dense, threshold seedi
 constexpr int FIXED_ROWS = 1024;    // chunk rows of the bounded-memory fallback / rescan passes
 constexpr int QUERY_BATCH = 65536;  // queries per workspace batch
 constexpr int STATE_OVERFLOW = 1;
-constexpr int SORT_BLOCK = 4096;    // rows are re-ordered (dense pattern, then length) inside blocks of this many consecutive rows
+constexpr int SORT_BLOCK = 4096;    // rows are re-ordered (by their weight sum) inside blocks of this many consecutive rows
 constexpr int POST_ROWS = 4096;     // row positions per posting block = u16 fixed-point accumulators per warp in k_post (8 KB)
 constexpr int POST_WARPS = 13;      // warps per CTA; two CTAs (26 warps, 213 KB of accumulators) per SM
 constexpr int POST_LIST = 32;       // per warp: rows of the swept block waiting for the full filter
@@ -97,8 +97,9 @@ struct Index {
     int64_t n_total = 0;
     uint64_t n_chunks = 0;
     // Rows are stored in a permuted order: inside every block of SORT_BLOCK consecutive rows they are sorted
-    // by their chunk count, so the 32 rows of a warp stream (nearly) the same number of chunks.  Everything
-    // indexed by "position" below uses that order; perm[position] is the shard-local original row.
+    // by their weight sum (which also sorts them by length, nearly: the 32 rows of a k_scan warp stream about the
+    // same number of chunks).  Everything indexed by "position" below uses that order; perm[position] is the
+    // shard-local original row.
     int32_t *perm = nullptr;        // [n_truth] position -> original row
     chunk_t *chunks = nullptr;      // [n_chunks] CHUNK_COLS ascending u16 column ids, sentinel = n_vocab
     uint32_t *chunk_ptr = nullptr;  // [n_truth + 1] by position
@@ -117,8 +118,7 @@ struct Index {
     float *sums_floor = nullptr;    // [n_sub * POST_GROUPS] smallest sums_pos of every group of 128 positions (+inf padded)
     int n_sub = 0;
     // Dense columns: the up to 32 columns with the highest document frequency (each in >= 1 / 128 of the rows) have no
-    // postings; which of them a row holds is a 32-bit pattern (bit 31 = the commonest column).  Rows are sorted by
-    // pattern inside their sort block, so 128 consecutive positions mostly share one pattern.
+    // postings; which of them a row holds is a 32-bit pattern (bit 31 = the commonest column).
     uint8_t *dense_bit = nullptr;   // [n_vocab + 1] bit of a dense column, 255 = not dense
     float *dense_w = nullptr;       // [32] w32 of the dense column of every bit (0 where unused)
     uint32_t *pat_pos = nullptr;    // [n_truth] dense pattern by position
@@ -197,28 +197,16 @@ __global__ void k_post_build(const uint16_t *__restrict__ packed, const uint32_t
     }
 }
 
-// one thread per row: chunk count and (optionally) sums_matrix_truth = sequential f32 sum in the
-// caller's column order (match_maker.py:172-174)
-__global__ void k_row_prepare(const int64_t *__restrict__ row_ptr, const uint16_t *__restrict__ cols,
-                              const float *__restrict__ w32, int n_vocab, int64_t n_rows, const int32_t *__restrict__ perm,
-                              const uint32_t *__restrict__ pat_row, uint32_t *__restrict__ pat_pos,
-                              uint32_t *__restrict__ n_chunks, float *__restrict__ sums, float *__restrict__ sums_pos,
-                              int compute_sums, int *__restrict__ not_monotone) {
+// one thread per row position: chunk count, row sum and dense pattern of the row that sits there
+__global__ void k_row_prepare(const int64_t *__restrict__ row_ptr, int64_t n_rows, const int32_t *__restrict__ perm,
+                              const uint32_t *__restrict__ pat_row, uint32_t *__restrict__ pat_pos, uint32_t *__restrict__ n_chunks,
+                              const float *__restrict__ sums, float *__restrict__ sums_pos) {
     int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= n_rows) return;
     const int64_t r = perm[pos];
     pat_pos[pos] = pat_row[r];
-    int64_t p0 = row_ptr[r], p1 = row_ptr[r + 1];
-    n_chunks[pos] = (uint32_t)((p1 - p0 + CHUNK_COLS - 1) / CHUNK_COLS);
-    float acc = 0.0f;
-    if (compute_sums) {
-        for (int64_t p = p0; p < p1; ++p) acc = __fadd_rn(acc, w32[min((int)cols[p], n_vocab)]);
-        sums[r] = acc;
-    } else {
-        acc = sums[r];
-    }
-    sums_pos[pos] = acc;
-    if (!(acc >= 0.0f)) atomicOr(not_monotone, 1);
+    n_chunks[pos] = (uint32_t)((row_ptr[r + 1] - row_ptr[r] + CHUNK_COLS - 1) / CHUNK_COLS);
+    sums_pos[pos] = sums[r];
 }
 
 // one warp per row: rank-sort the row's column ids ascending into its sentinel padded chunks
@@ -277,24 +265,35 @@ __global__ void k_col_df(const uint16_t *__restrict__ cols, int64_t nnz, int n_v
     if (i < nnz && cols[i] < n_vocab) atomicAdd(df + cols[i], 1u);
 }
 
-// Per original row: its dense pattern and the key its position inside the sort block is sorted by:
-// (sort block, pattern, chunk count) - the top field keeps every block of SORT_BLOCK rows in place.
-__global__ void k_row_keys(const int64_t *__restrict__ row_ptr, const uint16_t *__restrict__ cols, int n_vocab, int64_t n_rows,
-                           const uint8_t *__restrict__ dense_bit, uint32_t *__restrict__ pat_row, unsigned long long *__restrict__ keys,
-                           int32_t *__restrict__ ids) {
+// Per original row: sums_matrix_truth = sequential f32 sum in the caller's column order (match_maker.py:172-174; taken
+// as given when the caller provides it), its dense pattern, and the key its position inside the sort block is sorted
+// by: (sort block, row sum) - the top field keeps every block of SORT_BLOCK rows in place.  Rows of (nearly) equal sum
+// sit together, so the smallest sum of a group of 128 positions is close to every row's own and the group bars of
+// k_post are nearly as tight as the row tests.  (Sorting by pattern first was measured and dropped: a block of 4,096
+// rows holds ~1,300 distinct patterns, the runs are too short to help and they scatter the sums - 1,060 instead of
+// 180 rows per query end up above their group's bar at N = 200k.)
+__global__ void k_row_keys(const int64_t *__restrict__ row_ptr, const uint16_t *__restrict__ cols, const float *__restrict__ w32, int n_vocab,
+                           int64_t n_rows, const uint8_t *__restrict__ dense_bit, int compute_sums, float *__restrict__ sums,
+                           uint32_t *__restrict__ pat_row, unsigned long long *__restrict__ keys, int32_t *__restrict__ ids,
+                           int *__restrict__ not_monotone) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
     const int64_t p0 = row_ptr[r], p1 = row_ptr[r + 1];
     uint32_t pat = 0;
-    if (dense_bit != nullptr) {
-        for (int64_t p = p0; p < p1; ++p) {
-            const int bit = dense_bit[min((int)cols[p], n_vocab)];
-            if (bit != 255) pat |= 1u << bit;
-        }
+    float acc = 0.0f;
+    for (int64_t p = p0; p < p1; ++p) {
+        const int col = min((int)cols[p], n_vocab);
+        const int bit = dense_bit[col];
+        if (bit != 255) pat |= 1u << bit;
+        acc = __fadd_rn(acc, w32[col]);
     }
+    if (compute_sums) sums[r] = acc;
+    else acc = sums[r];
+    if (!(acc >= 0.0f)) atomicOr(not_monotone, 1);
     pat_row[r] = pat;
-    const unsigned long long chunks = (unsigned long long)min((long long)((p1 - p0 + CHUNK_COLS - 1) / CHUNK_COLS), 1023ll);
-    keys[r] = ((unsigned long long)(r / SORT_BLOCK) << 42) | ((unsigned long long)pat << 10) | chunks;
+    // 2^-10 units, saturating at 2^21 (sums are a few hundred at most)
+    const unsigned long long sum_key = (unsigned long long)(fminf(fmaxf(acc, 0.0f), 2097151.0f) * 1024.0f);
+    keys[r] = ((unsigned long long)(r / SORT_BLOCK) << 42) | sum_key;
     ids[r] = (int32_t)r;
 }
 
@@ -688,7 +687,6 @@ __global__ void __launch_bounds__(POST_WARPS * 32, POST_CTAS) k_post(PostParams 
     __syncthreads();
     const long long cta_first = (long long)blockIdx.x * p.tasks_per_cta;
     const int cta_tasks = (int)min((long long)p.tasks_per_cta, p.n_tasks - cta_first);
-    const unsigned lanes_below = (1u << lane) - 1u;
     const int stride = p.n_vocab + 1;
     const uint4 zero4 = make_uint4(0, 0, 0, 0);
     constexpr int SWEEPS = POST_ROWS / 256;   // the sweep takes 256 rows (8 per lane) at a time
@@ -910,27 +908,46 @@ __global__ void __launch_bounds__(POST_WARPS * 32, POST_CTAS) k_post(PostParams 
                     acc4[idx] = zero4;
                     continue;
                 }
+                // some row of these 256 is above its bar: every lane marks which of its 8 values are (they stay in the
+                // block for the full test, the others are cleared) and the lanes with marks take list slots in lane order
                 const uint32_t words[4] = {v.x, v.y, v.z, v.w};
                 uint32_t kept[4];
+                unsigned marks = 0;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const uint32_t lo = words[c] & 0xffffu, hi = words[c] >> 16;
-                    kept[c] = ((int)lo > bar ? lo : 0u) | ((int)hi > bar ? (hi << 16) : 0u);
+                    const bool lo_above = (int)lo > bar, hi_above = (int)hi > bar;
+                    kept[c] = (lo_above ? lo : 0u) | (hi_above ? (hi << 16) : 0u);
+                    marks |= (lo_above ? 1u : 0u) << (2 * c) | (hi_above ? 1u : 0u) << (2 * c + 1);
                 }
                 acc4[idx] = make_uint4(kept[0], kept[1], kept[2], kept[3]);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int value = (int)((words[c >> 1] >> ((c & 1) * 16)) & 0xffffu);
-                    const bool above = value > bar;
-                    const unsigned above_mask = __ballot_sync(0xffffffffu, above);
-                    if (above_mask == 0) continue;
-                    if (n_list + __popc(above_mask) > POST_LIST) {
-                        post_flush(acc, list, n_list, base_pos, pq.ab, pq.inv_scale, pq.grow, pq.mask, p.n_truth, p.pat_pos, p.sums, p.cand_count, p.cand,
-                                   p.cap, s_dense_w, b);
+                const int mine = __popc(marks);
+                int before = 0, total = 0;
+                for (unsigned holders = __ballot_sync(0xffffffffu, marks != 0); holders != 0; holders &= holders - 1) {
+                    const int src = __ffs(holders) - 1;
+                    const int count = __shfl_sync(0xffffffffu, mine, src);
+                    if (src < lane) before += count;
+                    total += count;
+                }
+                // the list holds POST_LIST rows; 256 candidates at once only happen with a negative bar
+                for (int first = 0; first < total; first += POST_LIST) {
+                    if (n_list > 0 && n_list + min(total - first, POST_LIST) > POST_LIST) {
+                        post_flush(acc, list, n_list, base_pos, pq.ab, pq.inv_scale, pq.grow, pq.mask, p.n_truth, p.pat_pos, p.sums, p.cand_count,
+                                   p.cand, p.cap, s_dense_w, b);
                         n_list = 0;
                     }
-                    if (above) list[n_list + __popc(above_mask & lanes_below)] = (uint16_t)(idx * 8 + c);
-                    n_list += __popc(above_mask);
+                    unsigned left = marks;
+                    for (int j = before; left != 0; ++j) {
+                        const int c = __ffs(left) - 1;
+                        left &= left - 1;
+                        if (j >= first && j < first + POST_LIST) list[n_list + j - first] = (uint16_t)(idx * 8 + c);
+                    }
+                    n_list += min(total - first, POST_LIST);
+                    if (first + POST_LIST < total) {
+                        post_flush(acc, list, n_list, base_pos, pq.ab, pq.inv_scale, pq.grow, pq.mask, p.n_truth, p.pat_pos, p.sums, p.cand_count,
+                                   p.cand, p.cap, s_dense_w, b);
+                        n_list = 0;
+                    }
                 }
             }
             if (n_list > 0) {
@@ -980,7 +997,42 @@ struct SelectParams {
 };
 
 // fast_jaccard's float32 sum for one (query, row) pair (match_maker.py:33-47): idf32 of the shared columns added in
-// ascending column id order - a merge of the query's ascending columns with the row's ascending chunks
+// ascending column id order.  The row's chunks are ascending, so walking them in order and looking every column up
+// in the query gives exactly that order.  Two forms of the lookup: a per-warp hash table of the query's columns in
+// shared memory (queries of <= SELECT_HASH_MAX columns: one or two probes per row column, no dependent global loads)
+// and a merge against the query's ascending column list in global memory.
+constexpr int SELECT_HASH = 256;       // slots per warp
+constexpr int SELECT_HASH_MAX = 128;   // most columns a hashed query may have (load factor 1/2)
+constexpr uint32_t SELECT_EMPTY = 0xffffffffu;
+__device__ __forceinline__ uint32_t select_hash(uint32_t col) { return (col * 0x9E3779B1u) >> 24; }
+
+__device__ __forceinline__ float exact_intersection_hashed(const uint32_t *h_key, const float *h_w, const chunk_t *__restrict__ chunks,
+                                                           uint32_t c0, uint32_t c1, int n_vocab) {
+    float sc = 0.0f;
+    chunk_t next = c0 < c1 ? __ldg(chunks + c0) : zero_chunk();
+    for (uint32_t c = c0; c < c1; ++c) {
+        const chunk_t ch = next;
+        if (c + 1 < c1) next = __ldg(chunks + c + 1);
+        const uint32_t words[CHUNK_COLS / 2] = {ch.x, ch.y};
+#pragma unroll
+        for (int k = 0; k < CHUNK_COLS; ++k) {
+            const uint32_t rc = (words[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+            if ((int)rc >= n_vocab) break;   // sentinel padding
+            uint32_t h = select_hash(rc);
+            for (;;) {
+                const uint32_t key = h_key[h];
+                if (key == rc) {
+                    sc = __fadd_rn(sc, h_w[h]);
+                    break;
+                }
+                if (key == SELECT_EMPTY) break;
+                h = (h + 1) & (SELECT_HASH - 1);
+            }
+        }
+    }
+    return sc;
+}
+
 __device__ __forceinline__ float exact_intersection(const uint16_t *__restrict__ q_cols, int g, const chunk_t *__restrict__ chunks, uint32_t c0,
                                                     uint32_t c1, const float *__restrict__ w32, int n_vocab) {
     float sc = 0.0f;
@@ -999,7 +1051,6 @@ __device__ __forceinline__ float exact_intersection(const uint16_t *__restrict__
     return sc;
 }
 
-
 __global__ void __launch_bounds__(128) k_select(SelectParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1007,6 +1058,8 @@ __global__ void __launch_bounds__(128) k_select(SelectParams p) {
     if (b >= p.n_batch) return;
     double *s_score = reinterpret_cast<double *>(smem) + (size_t)warp * p.max_items;
     int32_t *s_row = reinterpret_cast<int32_t *>(smem + (size_t)4 * p.max_items * 8) + (size_t)warp * p.max_items;
+    uint32_t *h_key = reinterpret_cast<uint32_t *>(smem + (size_t)4 * p.max_items * 12) + (size_t)warp * SELECT_HASH;   // rescore only
+    float *h_w = reinterpret_cast<float *>(smem + (size_t)4 * p.max_items * 12 + (size_t)4 * SELECT_HASH * 4) + (size_t)warp * SELECT_HASH;
     __shared__ double s_kth[4];
 
     if (p.state[b] & STATE_OVERFLOW) return;
@@ -1053,6 +1106,27 @@ __global__ void __launch_bounds__(128) k_select(SelectParams p) {
             }
             return;
         }
+        const int64_t q0 = p.q_ptr[q];
+        const int g = (int)(p.q_ptr[q + 1] - q0);
+        const bool hashed = p.rescore && g <= SELECT_HASH_MAX;
+        if (hashed) {   // the query's columns -> (column, idf32) hash table
+            for (int i = lane; i < SELECT_HASH; i += 32) h_key[i] = SELECT_EMPTY;
+            __syncwarp();
+            for (int i = lane; i < g; i += 32) {
+                const uint32_t col = p.q_sorted[q0 + i];
+                if ((int)col >= p.n_vocab) continue;
+                uint32_t h = select_hash(col);
+                for (;;) {
+                    const uint32_t old = atomicCAS(h_key + h, SELECT_EMPTY, col);
+                    if (old == SELECT_EMPTY || old == col) {
+                        h_w[h] = __ldg(p.w32 + col);
+                        break;
+                    }
+                    h = (h + 1) & (SELECT_HASH - 1);
+                }
+            }
+            __syncwarp();
+        }
         for (int i0 = 0; i0 < cnt; i0 += 32) {
             int i = i0 + lane;
             bool pass = false;
@@ -1061,11 +1135,8 @@ __global__ void __launch_bounds__(128) k_select(SelectParams p) {
             if (i < cnt) {
                 uint2 c = p.cand[(size_t)b * p.cap + i];
                 float sc = __uint_as_float(c.y);
-                if (p.rescore) {
-                    const int64_t q0 = p.q_ptr[q];
-                    sc = exact_intersection(p.q_sorted + q0, (int)(p.q_ptr[q + 1] - q0), p.chunks, p.chunk_ptr[c.x], p.chunk_ptr[c.x + 1],
-                                            p.w32, p.n_vocab);
-                }
+                if (hashed) sc = exact_intersection_hashed(h_key, h_w, p.chunks, p.chunk_ptr[c.x], p.chunk_ptr[c.x + 1], p.n_vocab);
+                else if (p.rescore) sc = exact_intersection(p.q_sorted + q0, g, p.chunks, p.chunk_ptr[c.x], p.chunk_ptr[c.x + 1], p.w32, p.n_vocab);
                 s = exact_score(sc, p.sums[c.x], mx);
                 row = p.perm[c.x];
                 pass = s > 0.0 && s >= theta;
@@ -1508,7 +1579,7 @@ static int launch_select(cudaStream_t stream, SelectParams sp) {
     while (widest < std::max(sp.cap, sp.dense_rows)) widest <<= 1;
     int items = widest + sp.m;
     sp.max_items = items;
-    size_t smem = (size_t)4 * items * 12;
+    size_t smem = (size_t)4 * items * 12 + (size_t)4 * SELECT_HASH * 8;
     DS_CHECK(ensure_dynamic_smem(reinterpret_cast<const void *>(&k_select), smem));
     k_select<<<(unsigned)ceil_div(sp.n_batch, 4), 128, smem, stream>>>(sp);
     DS_LAUNCHED("k_select");
@@ -1695,7 +1766,7 @@ static int run_batches(Workspace &ws, const Index &ix, const QuerySet &qs, const
         DS_CHECK(run_pipeline(ws, ix, qs, batch, mode, k, m, false, false, d_threshold, out, &overflowed));
     }
     // second try with 4,096-entry buffers (thousands of rows tied at the threshold, e.g. a title the truth DB repeats)
-    const bool wide_fits = (size_t)4 * (CAND_CAP_WIDE + m) * 12 <= 227 * 1024;   // k_select's shared memory (4 warps per CTA)
+    const bool wide_fits = (size_t)4 * (CAND_CAP_WIDE + m) * 12 + (size_t)4 * SELECT_HASH * 8 <= 227 * 1024;   // k_select's shared memory (4 warps per CTA)
     if (!wide_fits) still_overflowed.swap(overflowed);
     for (size_t i0 = 0; i0 < overflowed.size(); i0 += QUERY_BATCH / 8) {
         size_t i1 = std::min(overflowed.size(), i0 + QUERY_BATCH / 8);
@@ -1945,7 +2016,7 @@ int ds_index_create(ds_index **out, int device, int64_t n_truth, int32_t n_vocab
         DS_CUDA(cudaMemcpyAsync(ix.dense_bit, h_dense_bit.data(), (size_t)n_vocab + 1, cudaMemcpyHostToDevice, stream));
         DS_CUDA(cudaMemcpyAsync(ix.dense_w, h_dense_w, DENSE_MAX * 4, cudaMemcpyHostToDevice, stream));
 
-        // position -> original row: inside every block of SORT_BLOCK rows sorted by (dense pattern, chunk count)
+        // position -> original row: inside every block of SORT_BLOCK rows sorted by the row sum
         uint32_t *d_pat_row = nullptr;
         unsigned long long *d_keys = nullptr, *d_keys_sorted = nullptr;
         int32_t *d_ids = nullptr;
@@ -1957,7 +2028,10 @@ int ds_index_create(ds_index **out, int device, int64_t n_truth, int32_t n_vocab
         DS_CHECK(ws.alloc(&d_counts, (size_t)n_truth + 1));
         DS_CUDA(cudaMemsetAsync(d_counts, 0, ((size_t)n_truth + 1) * 4, stream));
         if (n_truth > 0) {
-            k_row_keys<<<(unsigned)ceil_div(n_truth, 256), 256, 0, stream>>>(d_ptr, d_cols, n_vocab, n_truth, ix.dense_bit, d_pat_row, d_keys, d_ids);
+            if (d_sums_in != nullptr)
+                DS_CUDA(cudaMemcpyAsync(ix.sums, d_sums_in, (size_t)n_truth * 4, cudaMemcpyDeviceToDevice, stream));
+            k_row_keys<<<(unsigned)ceil_div(n_truth, 256), 256, 0, stream>>>(d_ptr, d_cols, ix.w32, n_vocab, n_truth, ix.dense_bit,
+                                                                            d_sums_in == nullptr ? 1 : 0, ix.sums, d_pat_row, d_keys, d_ids, d_post_flags);
             DS_LAUNCHED("k_row_keys");
             int end_bit = 42;
             while (end_bit < 64 && ((int64_t)1 << (end_bit - 42)) <= ceil_div(n_truth, (int64_t)SORT_BLOCK)) ++end_bit;
@@ -1967,10 +2041,8 @@ int ds_index_create(ds_index **out, int device, int64_t n_truth, int32_t n_vocab
             DS_CHECK(ws.alloc(&d_sort_temp, sort_bytes));
             DS_CUDA(cub::DeviceRadixSort::SortPairs(d_sort_temp, sort_bytes, d_keys, d_keys_sorted, d_ids, ix.perm, (int)n_truth, 0, end_bit, stream));
             g_kernel_launches.fetch_add(1);
-            if (d_sums_in != nullptr)
-                DS_CUDA(cudaMemcpyAsync(ix.sums, d_sums_in, (size_t)n_truth * 4, cudaMemcpyDeviceToDevice, stream));
-            k_row_prepare<<<(unsigned)ceil_div(n_truth, 256), 256, 0, stream>>>(d_ptr, d_cols, ix.w32, n_vocab, n_truth, ix.perm, d_pat_row, ix.pat_pos,
-                                                                               d_counts, ix.sums, ix.sums_pos, d_sums_in == nullptr ? 1 : 0, d_post_flags);
+            k_row_prepare<<<(unsigned)ceil_div(n_truth, 256), 256, 0, stream>>>(d_ptr, n_truth, ix.perm, d_pat_row, ix.pat_pos, d_counts, ix.sums,
+                                                                               ix.sums_pos);
             DS_LAUNCHED("k_row_prepare");
         }
         size_t temp_bytes = 0;

@@ -40,6 +40,12 @@ METRICS = [
 ]
 
 
+SOURCES = {'k_post': ('ds_topn.cu', 'ds_common.cuh'), 'k_scan': ('ds_topn.cu', 'ds_common.cuh'), 'k_select': ('ds_topn.cu', 'ds_common.cuh'),
+           'k_indel_pairs': ('ds_pairs.cu', 'ds_common.cuh'), 'k_feature_words': ('ds_pairs.cu', 'ds_common.cuh'),
+           'k_query_pairs': ('ds_pairs.cu', 'ds_common.cuh'), 'k_query_features': ('ds_pairs.cu', 'ds_common.cuh')}
+WORKLOAD = os.environ.get('DS_PROFILE_WORKLOAD', 'bench.py --steps 1 --warmup 1 --no-cpu (C3: 100k x 500k synthetic, top-10)')
+
+
 def to_ms(value, unit):
     value = float(value.replace(',', ''))
     return {'ns': 1e-6, 'nsecond': 1e-6, 'us': 1e-3, 'usecond': 1e-3, 'ms': 1.0, 'msecond': 1.0, 's': 1e3}.get(unit, 1e-6) * value
@@ -93,6 +99,40 @@ def metrics(tag, report, kernel):
     json.dump({'kernel': kernel, 'dram_bytes_per_launch': sum(dram) / len(dram), 'captured_launches': dram,
                'source': f'profiles/{tag}_{kernel}_metrics.csv (ncu --set full --clock-control none)'},
               open(os.path.join(HERE, f'{kernel}_traffic.json'), 'w'), indent=1)
+
+    def mean_of(metric, scale=1.0):
+        if metric not in header:
+            return None
+        i = header.index(metric)
+        values = [float(r[i].replace(',', '')) for r in rows[2:] if r[i] not in ('', 'n/a')]
+        return sum(values) / len(values) * scale if values else None
+
+    def bytes_of(metric):
+        if metric not in header:
+            return None
+        i = header.index(metric)
+        values = [to_bytes(r[i], units[i]) for r in rows[2:] if r[i] not in ('', 'n/a')]
+        return sum(values) / len(values) if values else None
+    i_time = header.index('gpu__time_duration.sum')
+    # what bench.py reads for `roofline` (the measured limiter of the kernel), stamped with the kernel sources it is from
+    import hashlib
+    digest = hashlib.sha256()
+    for name in SOURCES.get(kernel, ('ds_topn.cu', 'ds_common.cuh')):
+        with open(os.path.join(ROOT, 'doppelspeller_b200', 'csrc', name), 'rb') as f:
+            digest.update(f.read())
+    json.dump({'kernel': kernel,
+               'smem_wavefronts_pct': mean_of('l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed'),
+               'issue_active_pct': mean_of('smsp__issue_active.avg.pct_of_peak_sustained_active'),
+               'dram_throughput_pct': mean_of('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'),
+               'warps_active_pct': mean_of('sm__warps_active.avg.pct_of_peak_sustained_active'),
+               'lsu_pipe_pct': mean_of('sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active'),
+               'alu_pipe_pct': mean_of('sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active'),
+               'l2_bytes_per_launch': bytes_of('lts__t_bytes.sum'), 'dram_bytes_per_launch': sum(dram) / len(dram),
+               'captured_launch_ms': sum(to_ms(r[i_time], units[i_time]) for r in rows[2:]) / len(rows[2:]),
+               'registers': mean_of('launch__registers_per_thread'), 'workload': WORKLOAD,
+               'source': f'profiles/{tag}_{kernel}_metrics.csv (ncu --set full --clock-control none --import-source on)',
+               'kernel_sources': digest.hexdigest()[:16]},
+              open(os.path.join(HERE, f'r2_{kernel}_ncu.json'), 'w'), indent=1)
 
 
 if __name__ == '__main__':
