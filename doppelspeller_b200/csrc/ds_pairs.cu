@@ -308,16 +308,17 @@ __device__ __forceinline__ int pair_class(int la, int lb, int mode) {
     return 3;
 }
 
-// sort key = (class << 10) | (la + lb); values = pair ids; counts per class
-__global__ void k_pair_keys(PairSource src, int64_t n, int mode, uint16_t *__restrict__ keys, int32_t *__restrict__ ids,
-                            int *__restrict__ counts) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// sort key = (class << 10) | (la + lb); values = pair ids; counts per class.  `subset` (nullable): only these pairs.
+__global__ void k_pair_keys(PairSource src, const int32_t *__restrict__ subset, int64_t n, int mode, uint16_t *__restrict__ keys,
+                            int32_t *__restrict__ ids, int *__restrict__ counts) {
+    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int cls = -1;
-    if (p < n) {
+    if (slot < n) {
+        const int64_t p = subset ? (int64_t)subset[slot] : slot;
         const int la = side_length(src.a, p), lb = side_length(src.b, p);
         cls = pair_class(la, lb, mode);
-        keys[p] = (uint16_t)((cls << 10) | min(la + lb, 1023));
-        ids[p] = (int32_t)p;
+        keys[slot] = (uint16_t)((cls << 10) | min(la + lb, 1023));
+        ids[slot] = (int32_t)p;
     }
     const int lane = threadIdx.x & 31;
 #pragma unroll
@@ -364,6 +365,120 @@ __global__ void __launch_bounds__(BLOCK) k_indel_pairs(PairSource src, const int
         else d = indel_true_dp(a, la, b, lb);
     }
     store_result<MODE>(out, total, d, p);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2 for candidate lists: consecutive pairs that share their first title (the top_n candidates of one test title,
+// predict.py:129-136).  One lane owns a chunk of consecutive pairs and keeps the match-mask table of the CURRENT
+// first title (pattern = that title, LCS is symmetric) in its private shared-memory column: the table is built once
+// per title instead of once per pair, nothing is sorted and no pair ids are gathered; the second title streams
+// through registers as aligned 32-bit words.  Pairs this path does not take (first title longer than 64 characters,
+// bytes outside the 40-symbol table, MODE 0 with la + lb > 255: the uint8 wrap region) go to `rest` and from there
+// through the sorted class kernels.
+// ---------------------------------------------------------------------------------------------------
+constexpr int CHUNK_BLOCK = 128;
+
+// counts the positions whose first title differs from the previous pair's (run structure of a pair list)
+__global__ void k_pair_runs(Side a, int64_t n, unsigned long long *__restrict__ changes) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool change = false;
+    if (p < n) {
+        if (a.stride > 0) change = true;   // padded rows: every pair has its own copy of the title
+        else change = p == 0 || a.idx[p] != a.idx[p - 1];
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, change);
+    if ((threadIdx.x & 31) == 0 && ballot != 0) atomicAdd(changes, (unsigned long long)__popc(ballot));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(CHUNK_BLOCK) k_indel_chunks(PairSource src, int64_t n, int chunk, K2Out out, int32_t *__restrict__ rest,
+                                                               int *__restrict__ rest_count) {
+    __shared__ u64 pm[PM_CODES * CHUNK_BLOCK];
+    u64 *my_pm = pm + threadIdx.x;
+    const int64_t first = ((int64_t)blockIdx.x * CHUNK_BLOCK + threadIdx.x) * chunk;
+    int64_t table_of = -1;    // title whose masks the column holds
+    bool table_ok = false;    // ... and whether this path can take it (<= 64 characters, all inside the table)
+    for (int j = 0; j < chunk; ++j) {
+        const int64_t p = first + j;
+        const bool active = p < n;
+        const uint8_t *pa = nullptr, *pb = nullptr;
+        int la = 0, lb = 0;
+        int64_t id_a = -1, id_b = -1;
+        if (active) {
+            load_side(src.a, p, &pa, &la, &id_a);
+            load_side(src.b, p, &pb, &lb, &id_b);
+            if (id_a != table_of) {
+                for (int c = 0; c < PM_CODES; ++c) my_pm[c * CHUNK_BLOCK] = 0;
+                bool good = la <= 64;
+                for (int i = 0; i < la && good; ++i) {
+                    const int c = table_code<MODE>(pa[i], good);
+                    if (good) my_pm[c * CHUNK_BLOCK] |= 1ull << i;
+                }
+                table_of = id_a;
+                table_ok = good;
+            }
+        }
+        const bool here = active && table_ok && lb <= 255 && (MODE == 1 || la + lb <= 255);
+        bool good = here;
+        int lcs = 0;
+        // 32-bit vectors while every lane of the warp has a pattern of <= 32 characters (85 % of real titles)
+        const bool narrow = __all_sync(0xffffffffu, !here || la <= 32);
+        if (here) {
+            const uintptr_t addr = reinterpret_cast<uintptr_t>(pb);
+            const int shift = (int)(addr & 3);
+            const uint32_t *g32 = reinterpret_cast<const uint32_t *>(addr - shift);
+            const int words_in = (shift + lb + 3) >> 2;
+            uint32_t cur = words_in > 0 ? __ldg(g32) : 0u;
+            uint32_t next = words_in > 1 ? __ldg(g32 + 1) : 0u;
+            if (narrow) {
+                const uint32_t *lo = reinterpret_cast<const uint32_t *>(my_pm);   // low halves of the 64-bit masks
+                uint32_t v = ~0u;
+                for (int j0 = 0, k = 0; j0 < lb; j0 += 4, ++k) {
+                    const uint32_t after = (k + 2 < words_in) ? __ldg(g32 + k + 2) : 0u;
+                    const uint32_t w = __funnelshift_r(cur, next, shift * 8);
+                    cur = next;
+                    next = after;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        if (j0 + t < lb) {
+                            bool in_table = true;
+                            const uint32_t mm = lo[table_code<MODE>((w >> (8 * t)) & 0xffu, in_table) * (2 * CHUNK_BLOCK)];
+                            good &= in_table;
+                            const uint32_t u = v & mm;
+                            v = (v + u) | (v & ~mm);
+                        }
+                    }
+                }
+                const uint32_t valid = (la >= 32) ? ~0u : ((1u << la) - 1);
+                lcs = __popc(~v & valid);
+            } else {
+                u64 v = ~0ull;
+                for (int j0 = 0, k = 0; j0 < lb; j0 += 4, ++k) {
+                    const uint32_t after = (k + 2 < words_in) ? __ldg(g32 + k + 2) : 0u;
+                    const uint32_t w = __funnelshift_r(cur, next, shift * 8);
+                    cur = next;
+                    next = after;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        if (j0 + t < lb) {
+                            bool in_table = true;
+                            const u64 mm = my_pm[table_code<MODE>((w >> (8 * t)) & 0xffu, in_table) * CHUNK_BLOCK];
+                            good &= in_table;
+                            const u64 u = v & mm;
+                            v = (v + u) | (v & ~mm);
+                        }
+                    }
+                }
+                const u64 valid = (la >= 64) ? ~0ull : ((1ull << la) - 1);
+                lcs = __popcll(~v & valid);
+            }
+        }
+        if (good) {
+            store_result<MODE>(out, la + lb, la + lb - 2 * lcs, p);
+        } else if (active) {
+            rest[atomicAdd(rest_count, 1)] = (int32_t)p;
+        }
+    }
 }
 
 // class 3 (MODE 0, la + lb > 255): the literal uint8 DP of feature_engineering.py:42-61, one pair per warp.
@@ -625,8 +740,9 @@ static int launch_indel_class(const PairSource &src, const int32_t *list, int64_
     return DS_OK;
 }
 
+// the sorted class pipeline over all n pairs (subset == nullptr) or over the listed pair ids
 template <int MODE>
-static int launch_indel_mode(Workspace &ws, const PairSource &src, int64_t n, const K2Out &out) {
+static int launch_indel_sorted(Workspace &ws, const PairSource &src, const int32_t *subset, int64_t n, const K2Out &out) {
     cudaStream_t stream = ws.stream();
     if (n <= 0) return DS_OK;
     if (n > INT32_MAX) return fail(DS_ERR_UNSUPPORTED, "more than 2^31-1 pairs per call");
@@ -639,7 +755,7 @@ static int launch_indel_mode(Workspace &ws, const PairSource &src, int64_t n, co
     DS_CHECK(ws.alloc(&d_ids_sorted, (size_t)n));
     DS_CHECK(ws.alloc(&d_counts, 4));
     DS_CUDA(cudaMemsetAsync(d_counts, 0, 4 * sizeof(int), stream));
-    k_pair_keys<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(src, n, MODE, d_keys, d_ids, d_counts);
+    k_pair_keys<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(src, subset, n, MODE, d_keys, d_ids, d_counts);
     DS_LAUNCHED("k_pair_keys");
     size_t temp_bytes = 0;
     DS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, d_keys, d_keys_sorted, d_ids, d_ids_sorted, (int)n, 0, 12, stream));
@@ -659,6 +775,39 @@ static int launch_indel_mode(Workspace &ws, const PairSource &src, int64_t n, co
         k_indel_wrap<<<(unsigned)ceil_div(h[3], 4), 128, 0, stream>>>(src, list + h[0] + h[1] + h[2], h[3], out);
         DS_LAUNCHED("k_indel_wrap");
     }
+    return DS_OK;
+}
+
+// Candidate lists (runs of pairs sharing their first title, at least 4 pairs per title on average) take the chunked
+// kernel; whatever it leaves and every other pair list takes the sorted class pipeline.
+template <int MODE>
+static int launch_indel_mode(Workspace &ws, const PairSource &src, int64_t n, const K2Out &out) {
+    cudaStream_t stream = ws.stream();
+    if (n <= 0) return DS_OK;
+    if (n > INT32_MAX) return fail(DS_ERR_UNSUPPORTED, "more than 2^31-1 pairs per call");
+    if (src.a.stride > 0 || n < 1024) return launch_indel_sorted<MODE>(ws, src, nullptr, n, out);
+    unsigned long long *d_changes = nullptr;
+    DS_CHECK(ws.alloc(&d_changes, 1));
+    DS_CUDA(cudaMemsetAsync(d_changes, 0, 8, stream));
+    k_pair_runs<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(src.a, n, d_changes);
+    DS_LAUNCHED("k_pair_runs");
+    unsigned long long h_changes = 0;
+    DS_CUDA(cudaMemcpyAsync(&h_changes, d_changes, 8, cudaMemcpyDeviceToHost, stream));
+    DS_CUDA(cudaStreamSynchronize(stream));
+    if (h_changes * 4 > (unsigned long long)n) return launch_indel_sorted<MODE>(ws, src, nullptr, n, out);
+    const int chunk = (int)std::min<int64_t>(32, std::max<int64_t>(4, (n + (int64_t)h_changes / 2) / (int64_t)std::max<unsigned long long>(1, h_changes)));
+    int32_t *d_rest = nullptr;
+    int *d_rest_count = nullptr;
+    DS_CHECK(ws.alloc(&d_rest, (size_t)n));
+    DS_CHECK(ws.alloc(&d_rest_count, 1));
+    DS_CUDA(cudaMemsetAsync(d_rest_count, 0, 4, stream));
+    const int64_t lanes = ceil_div(n, chunk);
+    k_indel_chunks<MODE><<<(unsigned)ceil_div(lanes, CHUNK_BLOCK), CHUNK_BLOCK, 0, stream>>>(src, n, chunk, out, d_rest, d_rest_count);
+    DS_LAUNCHED("k_indel_chunks");
+    int h_rest = 0;
+    DS_CUDA(cudaMemcpyAsync(&h_rest, d_rest_count, 4, cudaMemcpyDeviceToHost, stream));
+    DS_CUDA(cudaStreamSynchronize(stream));
+    if (h_rest > 0) DS_CHECK(launch_indel_sorted<MODE>(ws, src, d_rest, h_rest, out));
     return DS_OK;
 }
 

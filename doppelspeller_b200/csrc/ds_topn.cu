@@ -646,17 +646,34 @@ __device__ __forceinline__ bool post_test(int acc, float gain, float bar, const 
     return upper > bar;
 }
 
+// what the rare paths of k_post need from the kernel parameters, kept in shared memory so that the hot loops do not
+// re-load them from the constant bank around every (inlined or not) call
+struct PostShared {
+    int64_t n_truth;
+    const uint32_t *pat_pos;
+    const float *sums;
+    int *cand_count;
+    uint2 *cand;
+    int cap;
+    float dense_w[DENSE_MAX];
+};
+
 // full test for the listed rows of a swept block (kept out of line: the sweep loop stays small)
-__device__ __noinline__ void post_flush(post_acc_t *acc, const uint16_t *list, int n_list, int64_t base_pos, float2 ab, float inv_scale,
-                                        float grow, uint32_t mask, int64_t n_truth, const uint32_t *__restrict__ pat_pos,
-                                        const float *__restrict__ sums, int *cand_count, uint2 *cand, int cap,
-                                        const float *s_dense_w, int b) {
-    const int lane = threadIdx.x & 31;
+__device__ __noinline__ void post_flush(post_acc_t *acc, const uint16_t *list, int n_list, int base_block, float2 ab, float inv_scale,
+                                        float grow, uint32_t mask, const PostShared *sh, int b, int lane) {
     PostQuery q;
     q.ab = ab;
     q.inv_scale = inv_scale;
     q.grow = grow;
     q.mask = mask;
+    const int64_t base_pos = (int64_t)base_block * POST_ROWS;
+    const int64_t n_truth = sh->n_truth;
+    const uint32_t *__restrict__ pat_pos = sh->pat_pos;
+    const float *__restrict__ sums = sh->sums;
+    int *cand_count = sh->cand_count;
+    uint2 *cand = sh->cand;
+    const int cap = sh->cap;
+    const float *s_dense_w = sh->dense_w;
     __syncwarp();
     for (int i = lane; i < n_list; i += 32) {
         const int r = list[i];
@@ -676,14 +693,23 @@ __device__ __noinline__ void post_flush(post_acc_t *acc, const uint16_t *list, i
 __global__ void __launch_bounds__(POST_WARPS * 32, POST_CTAS) k_post(PostParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_next;
-    __shared__ float s_dense_w[DENSE_MAX];
+    __shared__ PostShared s_shared;
+    const float *s_dense_w = s_shared.dense_w;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     post_acc_t *acc = reinterpret_cast<post_acc_t *>(smem) + (size_t)warp * POST_ROWS;
     uint4 *acc4 = reinterpret_cast<uint4 *>(acc);
     uint16_t *list = reinterpret_cast<uint16_t *>(smem + (size_t)POST_WARPS * POST_ROWS * sizeof(post_acc_t)) + warp * POST_LIST;
     uint2 *desc = reinterpret_cast<uint2 *>(smem + (size_t)POST_WARPS * (POST_ROWS * sizeof(post_acc_t) + POST_LIST * 2)) + warp * POST_DESC;
-    if (threadIdx.x == 0) s_next = 0;
-    if (threadIdx.x < DENSE_MAX) s_dense_w[threadIdx.x] = p.dense_w[threadIdx.x];
+    if (threadIdx.x == 0) {
+        s_next = 0;
+        s_shared.n_truth = p.n_truth;
+        s_shared.pat_pos = p.pat_pos;
+        s_shared.sums = p.sums;
+        s_shared.cand_count = p.cand_count;
+        s_shared.cand = p.cand;
+        s_shared.cap = p.cap;
+    }
+    if (threadIdx.x < DENSE_MAX) s_shared.dense_w[threadIdx.x] = p.dense_w[threadIdx.x];
     __syncthreads();
     const long long cta_first = (long long)blockIdx.x * p.tasks_per_cta;
     const int cta_tasks = (int)min((long long)p.tasks_per_cta, p.n_tasks - cta_first);
@@ -881,7 +907,7 @@ __global__ void __launch_bounds__(POST_WARPS * 32, POST_CTAS) k_post(PostParams 
                             post_acc_t *slot0 = acc + ring[d].r0, *slot1 = acc + ring[d].r1;
                             const bool first = lane < n, second = lane + 32 < n;
                             uint32_t a0 = 0, a1 = 0;
-                            if (first) a0 = *slot0;
+                            if (first) a0 = *slot0;      // predicated: idle lanes would only add bank conflicts
                             if (second) a1 = *slot1;
                             if (index + POST_DEPTH < n_pieces) fetch(index + POST_DEPTH, ring[d]);
                             if (first) *slot0 = (post_acc_t)(a0 + add);
@@ -895,8 +921,7 @@ __global__ void __launch_bounds__(POST_WARPS * 32, POST_CTAS) k_post(PostParams 
 
             // sweep and zero the block, 256 rows (8 per lane, one 128-bit load) at a time; rows above their group's bar
             // wait in `list` (their accumulators stay) for the full test
-            const int64_t base_pos = (int64_t)s * POST_ROWS;
-#pragma unroll 2
+#pragma unroll 4
             for (int i = 0; i < SWEEPS; ++i) {
                 const int idx = i * 32 + lane;
                 const int bar = __shfl_sync(0xffffffffu, my_bar, 2 * i + (lane >> 4));   // lanes 0-15 / 16-31: two groups
@@ -932,8 +957,7 @@ __global__ void __launch_bounds__(POST_WARPS * 32, POST_CTAS) k_post(PostParams 
                 // the list holds POST_LIST rows; 256 candidates at once only happen with a negative bar
                 for (int first = 0; first < total; first += POST_LIST) {
                     if (n_list > 0 && n_list + min(total - first, POST_LIST) > POST_LIST) {
-                        post_flush(acc, list, n_list, base_pos, pq.ab, pq.inv_scale, pq.grow, pq.mask, p.n_truth, p.pat_pos, p.sums, p.cand_count,
-                                   p.cand, p.cap, s_dense_w, b);
+                        post_flush(acc, list, n_list, s, pq.ab, pq.inv_scale, pq.grow, pq.mask, &s_shared, b, lane);
                         n_list = 0;
                     }
                     unsigned left = marks;
@@ -944,15 +968,13 @@ __global__ void __launch_bounds__(POST_WARPS * 32, POST_CTAS) k_post(PostParams 
                     }
                     n_list += min(total - first, POST_LIST);
                     if (first + POST_LIST < total) {
-                        post_flush(acc, list, n_list, base_pos, pq.ab, pq.inv_scale, pq.grow, pq.mask, p.n_truth, p.pat_pos, p.sums, p.cand_count,
-                                   p.cand, p.cap, s_dense_w, b);
+                        post_flush(acc, list, n_list, s, pq.ab, pq.inv_scale, pq.grow, pq.mask, &s_shared, b, lane);
                         n_list = 0;
                     }
                 }
             }
             if (n_list > 0) {
-                post_flush(acc, list, n_list, base_pos, pq.ab, pq.inv_scale, pq.grow, pq.mask, p.n_truth, p.pat_pos, p.sums, p.cand_count, p.cand,
-                                   p.cap, s_dense_w, b);
+                post_flush(acc, list, n_list, s, pq.ab, pq.inv_scale, pq.grow, pq.mask, &s_shared, b, lane);
                 n_list = 0;
             }
             __syncwarp();
