@@ -330,7 +330,10 @@ __global__ void k_pair_keys(PairSource src, const int32_t *__restrict__ subset, 
 
 // classes 0..2: one pair per lane.  W/MAXLEN select the path: <u32,64> class 0, <u64,64> class 1, <u64,255> class 2
 template <typename W, int MAXLEN, int BLOCK, int MODE>
-__global__ void __launch_bounds__(BLOCK) k_indel_pairs(PairSource src, const int32_t *__restrict__ pair_list, int64_t n, K2Out out) {
+__global__ void __launch_bounds__(BLOCK) k_indel_pairs(PairSource src, const int32_t *__restrict__ pair_list, int64_t n, K2Out out,
+                                                       const int *__restrict__ n_device = nullptr) {
+    if (n_device != nullptr) n = min(n, (int64_t)*n_device);   // list filled on the device: its length never visits the host
+    if ((int64_t)blockIdx.x * BLOCK >= n) return;
     extern __shared__ __align__(16) unsigned char k2_raw[];
     typedef K2Smem<W, MAXLEN, BLOCK> Smem;
     Smem &sm = *reinterpret_cast<Smem *>(k2_raw);
@@ -368,15 +371,15 @@ __global__ void __launch_bounds__(BLOCK) k_indel_pairs(PairSource src, const int
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K2 for candidate lists: consecutive pairs that share their first title (the top_n candidates of one test title,
-// predict.py:129-136).  One lane owns a chunk of consecutive pairs and keeps the match-mask table of the CURRENT
-// first title (pattern = that title, LCS is symmetric) in its private shared-memory column: the table is built once
-// per title instead of once per pair, nothing is sorted and no pair ids are gathered; the second title streams
-// through registers as aligned 32-bit words.  Pairs this path does not take (first title longer than 64 characters,
-// bytes outside the 40-symbol table, MODE 0 with la + lb > 255: the uint8 wrap region) go to `rest` and from there
-// through the sorted class kernels.
+// K2 for candidate lists: runs of `run` consecutive pairs that share their first title (the top_n candidates of one
+// test title, predict.py:129-136; uniform run length: a [Q, top_n] list).  A group of 16 lanes (32 for runs longer
+// than 16) takes one run: the match-mask table of the shared title is built ONCE per run in shared memory by the
+// group (pattern = that title; the LCS is symmetric), every lane then streams its own second title through registers
+// as aligned 32-bit words.  Nothing is sorted, no pair ids are gathered.  Pairs this path does not take (a run whose
+// pairs do not all share the title, a first title longer than 64 characters, bytes outside the 40-symbol table, MODE 0
+// with la + lb > 255: the uint8 wrap region) go to `rest` and from there through the sorted class kernels.
 // ---------------------------------------------------------------------------------------------------
-constexpr int CHUNK_BLOCK = 128;
+constexpr int GROUP_BLOCK = 256;
 
 // counts the positions whose first title differs from the previous pair's (run structure of a pair list)
 __global__ void k_pair_runs(Side a, int64_t n, unsigned long long *__restrict__ changes) {
@@ -391,38 +394,55 @@ __global__ void k_pair_runs(Side a, int64_t n, unsigned long long *__restrict__ 
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(CHUNK_BLOCK) k_indel_chunks(PairSource src, int64_t n, int chunk, K2Out out, int32_t *__restrict__ rest,
+__global__ void __launch_bounds__(GROUP_BLOCK) k_indel_groups(PairSource src, int64_t n, int run, int group_lanes, K2Out out,
+                                                               int32_t *__restrict__ rest, int32_t *__restrict__ rest_wrap,
                                                                int *__restrict__ rest_count) {
-    __shared__ u64 pm[PM_CODES * CHUNK_BLOCK];
-    u64 *my_pm = pm + threadIdx.x;
-    const int64_t first = ((int64_t)blockIdx.x * CHUNK_BLOCK + threadIdx.x) * chunk;
-    int64_t table_of = -1;    // title whose masks the column holds
-    bool table_ok = false;    // ... and whether this path can take it (<= 64 characters, all inside the table)
-    for (int j = 0; j < chunk; ++j) {
-        const int64_t p = first + j;
-        const bool active = p < n;
-        const uint8_t *pa = nullptr, *pb = nullptr;
-        int la = 0, lb = 0;
-        int64_t id_a = -1, id_b = -1;
+    // group_lanes = min(run, 32) consecutive lanes take one run; a warp holds 32 / group_lanes runs (30 of 32 lanes busy at
+    // top_n = 10); runs longer than 32 pairs go through their group in rounds
+    constexpr int WARPS = GROUP_BLOCK / 32;
+    __shared__ __align__(8) uint32_t pm[WARPS * 8][PM_CODES][2];   // per group (>= 4 lanes: <= 8 per warp): [code][low / high 32 positions]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int GROUP = group_lanes;
+    const int per_warp = 32 / GROUP;
+    const int group_in_warp = lane / GROUP;
+    const int sub = lane - group_in_warp * GROUP;   // lane inside the group
+    if (group_in_warp >= per_warp) return;          // the warp's spare lanes
+    const unsigned group_mask = (GROUP == 32 ? 0xffffffffu : ((1u << GROUP) - 1u)) << (group_in_warp * GROUP);
+    const int64_t r = ((int64_t)blockIdx.x * WARPS + warp) * per_warp + group_in_warp;
+    const int64_t first = r * run;
+    if (first >= n) return;                         // whole groups leave together
+    uint32_t(*my_pm)[2] = pm[warp * 8 + group_in_warp];
+    for (int c = sub; c < PM_CODES; c += GROUP) {
+        my_pm[c][0] = 0;
+        my_pm[c][1] = 0;
+    }
+    const uint8_t *pa = nullptr;
+    int la = 0;
+    int64_t id_a = -1;
+    load_side(src.a, first, &pa, &la, &id_a);
+    __syncwarp(group_mask);
+    bool good = la <= 64;
+    for (int i = sub; i < la && i < 64; i += GROUP) {
+        const int c = table_code<MODE>(pa[i], good);
+        atomicOr(&my_pm[c][i >> 5], 1u << (i & 31));
+    }
+    __syncwarp(group_mask);
+    const bool table_ok = __all_sync(group_mask, good);
+    const bool narrow = la <= 32;                   // uniform inside the group
+    for (int j0 = 0; j0 < run; j0 += GROUP) {
+        const int64_t p = first + j0 + sub;
+        const bool active = j0 + sub < run && p < n;
+        const uint8_t *pb = nullptr;
+        int lb = 0;
+        bool here = false;
         if (active) {
-            load_side(src.a, p, &pa, &la, &id_a);
+            int64_t id_b = -1;
             load_side(src.b, p, &pb, &lb, &id_b);
-            if (id_a != table_of) {
-                for (int c = 0; c < PM_CODES; ++c) my_pm[c * CHUNK_BLOCK] = 0;
-                bool good = la <= 64;
-                for (int i = 0; i < la && good; ++i) {
-                    const int c = table_code<MODE>(pa[i], good);
-                    if (good) my_pm[c * CHUNK_BLOCK] |= 1ull << i;
-                }
-                table_of = id_a;
-                table_ok = good;
-            }
+            const bool same_title = src.a.stride > 0 ? false : src.a.idx[p] == (int32_t)id_a;
+            here = table_ok && same_title && lb <= 255 && (MODE == 1 || la + lb <= 255);
         }
-        const bool here = active && table_ok && lb <= 255 && (MODE == 1 || la + lb <= 255);
-        bool good = here;
+        bool ok = here;
         int lcs = 0;
-        // 32-bit vectors while every lane of the warp has a pattern of <= 32 characters (85 % of real titles)
-        const bool narrow = __all_sync(0xffffffffu, !here || la <= 32);
         if (here) {
             const uintptr_t addr = reinterpret_cast<uintptr_t>(pb);
             const int shift = (int)(addr & 3);
@@ -431,19 +451,18 @@ __global__ void __launch_bounds__(CHUNK_BLOCK) k_indel_chunks(PairSource src, in
             uint32_t cur = words_in > 0 ? __ldg(g32) : 0u;
             uint32_t next = words_in > 1 ? __ldg(g32 + 1) : 0u;
             if (narrow) {
-                const uint32_t *lo = reinterpret_cast<const uint32_t *>(my_pm);   // low halves of the 64-bit masks
                 uint32_t v = ~0u;
-                for (int j0 = 0, k = 0; j0 < lb; j0 += 4, ++k) {
+                for (int t0 = 0, k = 0; t0 < lb; t0 += 4, ++k) {
                     const uint32_t after = (k + 2 < words_in) ? __ldg(g32 + k + 2) : 0u;
                     const uint32_t w = __funnelshift_r(cur, next, shift * 8);
                     cur = next;
                     next = after;
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
-                        if (j0 + t < lb) {
+                        if (t0 + t < lb) {
                             bool in_table = true;
-                            const uint32_t mm = lo[table_code<MODE>((w >> (8 * t)) & 0xffu, in_table) * (2 * CHUNK_BLOCK)];
-                            good &= in_table;
+                            const uint32_t mm = my_pm[table_code<MODE>((w >> (8 * t)) & 0xffu, in_table)][0];
+                            ok &= in_table;
                             const uint32_t u = v & mm;
                             v = (v + u) | (v & ~mm);
                         }
@@ -453,17 +472,18 @@ __global__ void __launch_bounds__(CHUNK_BLOCK) k_indel_chunks(PairSource src, in
                 lcs = __popc(~v & valid);
             } else {
                 u64 v = ~0ull;
-                for (int j0 = 0, k = 0; j0 < lb; j0 += 4, ++k) {
+                for (int t0 = 0, k = 0; t0 < lb; t0 += 4, ++k) {
                     const uint32_t after = (k + 2 < words_in) ? __ldg(g32 + k + 2) : 0u;
                     const uint32_t w = __funnelshift_r(cur, next, shift * 8);
                     cur = next;
                     next = after;
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
-                        if (j0 + t < lb) {
+                        if (t0 + t < lb) {
                             bool in_table = true;
-                            const u64 mm = my_pm[table_code<MODE>((w >> (8 * t)) & 0xffu, in_table) * CHUNK_BLOCK];
-                            good &= in_table;
+                            const uint2 m2 = *reinterpret_cast<const uint2 *>(my_pm[table_code<MODE>((w >> (8 * t)) & 0xffu, in_table)]);
+                            ok &= in_table;
+                            const u64 mm = ((u64)m2.y << 32) | m2.x;
                             const u64 u = v & mm;
                             v = (v + u) | (v & ~mm);
                         }
@@ -473,10 +493,13 @@ __global__ void __launch_bounds__(CHUNK_BLOCK) k_indel_chunks(PairSource src, in
                 lcs = __popcll(~v & valid);
             }
         }
-        if (good) {
+        if (ok) {
             store_result<MODE>(out, la + lb, la + lb - 2 * lcs, p);
         } else if (active) {
-            rest[atomicAdd(rest_count, 1)] = (int32_t)p;
+            // the pair's own first title decides where it goes on (it may differ from the group's)
+            const int my_la = side_length(src.a, p);
+            if (MODE == 0 && (my_la + lb > 255 || max(my_la, lb) > 255)) rest_wrap[atomicAdd(rest_count + 1, 1)] = (int32_t)p;
+            else rest[atomicAdd(rest_count, 1)] = (int32_t)p;
         }
     }
 }
@@ -492,12 +515,13 @@ struct WrapSmem {
     uint8_t edge[2][MAX_LONG + 8];
 };
 
-__global__ void __launch_bounds__(128) k_indel_wrap(PairSource src, const int32_t *__restrict__ pair_list, int64_t n, K2Out out) {
+__global__ void __launch_bounds__(128) k_indel_wrap(PairSource src, const int32_t *__restrict__ pair_list, int64_t n, K2Out out,
+                                                    const int *__restrict__ n_device = nullptr) {
+    if (n_device != nullptr) n = min(n, (int64_t)*n_device);
     __shared__ WrapSmem smem[4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t slot = (int64_t)blockIdx.x * 4 + warp;
-    if (slot >= n) return;
     WrapSmem &sm = smem[warp];
+    for (int64_t slot = (int64_t)blockIdx.x * 4 + warp; slot < n; slot += (int64_t)gridDim.x * 4) {
     const int64_t p = pair_list ? (int64_t)pair_list[slot] : slot;
     const uint8_t *a, *b;
     int la, lb;
@@ -540,6 +564,8 @@ __global__ void __launch_bounds__(128) k_indel_wrap(PairSource src, const int32_
         cur_edge ^= 1;
     }
     if (lane == 0) store_result<0>(out, la + lb, result, p);
+    __syncwarp();
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -772,14 +798,14 @@ static int launch_indel_sorted(Workspace &ws, const PairSource &src, const int32
     DS_CHECK((launch_indel_class<u64, 255, 64, MODE>(src, list + h[0] + h[1], h[2], out, stream)));
     if (h[3] > 0) {
         if (MODE != 0) return fail(DS_ERR_UNSUPPORTED, "strings longer than 255 bytes");
-        k_indel_wrap<<<(unsigned)ceil_div(h[3], 4), 128, 0, stream>>>(src, list + h[0] + h[1] + h[2], h[3], out);
+        k_indel_wrap<<<(unsigned)std::min<int64_t>(ceil_div(h[3], 4), 148 * 16), 128, 0, stream>>>(src, list + h[0] + h[1] + h[2], h[3], out);
         DS_LAUNCHED("k_indel_wrap");
     }
     return DS_OK;
 }
 
-// Candidate lists (runs of pairs sharing their first title, at least 4 pairs per title on average) take the chunked
-// kernel; whatever it leaves and every other pair list takes the sorted class pipeline.
+// Candidate lists (uniform runs of pairs sharing their first title) take the grouped kernel; whatever it leaves and
+// every other pair list takes the sorted class pipeline.
 template <int MODE>
 static int launch_indel_mode(Workspace &ws, const PairSource &src, int64_t n, const K2Out &out) {
     cudaStream_t stream = ws.stream();
@@ -794,20 +820,36 @@ static int launch_indel_mode(Workspace &ws, const PairSource &src, int64_t n, co
     unsigned long long h_changes = 0;
     DS_CUDA(cudaMemcpyAsync(&h_changes, d_changes, 8, cudaMemcpyDeviceToHost, stream));
     DS_CUDA(cudaStreamSynchronize(stream));
-    if (h_changes * 4 > (unsigned long long)n) return launch_indel_sorted<MODE>(ws, src, nullptr, n, out);
-    const int chunk = (int)std::min<int64_t>(32, std::max<int64_t>(4, (n + (int64_t)h_changes / 2) / (int64_t)std::max<unsigned long long>(1, h_changes)));
-    int32_t *d_rest = nullptr;
-    int *d_rest_count = nullptr;
+    // uniform runs of at least 4 pairs (a [Q, top_n] candidate list) take the grouped kernel; the kernel itself sends every
+    // run that turns out not to share its title to `rest`, so a wrong guess costs time, never correctness
+    if (h_changes == 0 || (unsigned long long)n % h_changes != 0 || h_changes * 4 > (unsigned long long)n)
+        return launch_indel_sorted<MODE>(ws, src, nullptr, n, out);
+    const int64_t run = n / (int64_t)h_changes;
+    if (run > 4096) return launch_indel_sorted<MODE>(ws, src, nullptr, n, out);
+    int32_t *d_rest = nullptr, *d_rest_wrap = nullptr;
+    int *d_rest_count = nullptr;   // [0] general, [1] uint8 wrap region
     DS_CHECK(ws.alloc(&d_rest, (size_t)n));
-    DS_CHECK(ws.alloc(&d_rest_count, 1));
-    DS_CUDA(cudaMemsetAsync(d_rest_count, 0, 4, stream));
-    const int64_t lanes = ceil_div(n, chunk);
-    k_indel_chunks<MODE><<<(unsigned)ceil_div(lanes, CHUNK_BLOCK), CHUNK_BLOCK, 0, stream>>>(src, n, chunk, out, d_rest, d_rest_count);
-    DS_LAUNCHED("k_indel_chunks");
-    int h_rest = 0;
-    DS_CUDA(cudaMemcpyAsync(&h_rest, d_rest_count, 4, cudaMemcpyDeviceToHost, stream));
-    DS_CUDA(cudaStreamSynchronize(stream));
-    if (h_rest > 0) DS_CHECK(launch_indel_sorted<MODE>(ws, src, d_rest, h_rest, out));
+    DS_CHECK(ws.alloc(&d_rest_wrap, (size_t)n));
+    DS_CHECK(ws.alloc(&d_rest_count, 2));
+    DS_CUDA(cudaMemsetAsync(d_rest_count, 0, 8, stream));
+    const int group_lanes = (int)std::max<int64_t>(4, std::min<int64_t>(run, 32));   // run >= 4 here
+    const int runs_per_block = (GROUP_BLOCK / 32) * (32 / group_lanes);
+    k_indel_groups<MODE><<<(unsigned)ceil_div((int64_t)h_changes, runs_per_block), GROUP_BLOCK, 0, stream>>>(src, n, (int)run, group_lanes, out,
+                                                                                                        d_rest, d_rest_wrap, d_rest_count);
+    DS_LAUNCHED("k_indel_groups");
+    // The leftovers (a fraction of a percent: long first titles, foreign bytes, the wrap region) take the general
+    // block kernel / the wrap kernel unsorted.  The list lengths stay on the device: the grids are sized for n and
+    // the blocks past the end of a list leave at once.
+    {
+        const size_t smem = sizeof(K2Smem<u64, 255, 64>);
+        DS_CHECK((ensure_dynamic_smem(reinterpret_cast<const void *>(&k_indel_pairs<u64, 255, 64, MODE>), smem)));
+        k_indel_pairs<u64, 255, 64, MODE><<<(unsigned)ceil_div(n, 64), 64, smem, stream>>>(src, d_rest, n, out, d_rest_count);
+        DS_LAUNCHED("k_indel_pairs");
+        if (MODE == 0) {
+            k_indel_wrap<<<(unsigned)std::min<int64_t>(ceil_div(n, 4), 148 * 8), 128, 0, stream>>>(src, d_rest_wrap, n, out, d_rest_count + 1);
+            DS_LAUNCHED("k_indel_wrap");
+        }
+    }
     return DS_OK;
 }
 

@@ -120,8 +120,10 @@ def encode_reference_order(data_n_grams, truth_n_grams):
                 q_cols=q_cols)
 
 
-def finish_index(enc):
-    """From an encoded index (column ids + per-row order given) derive what fast_jaccard consumes:
+def finish_index(enc, queries=None):
+    """From an encoded index (column ids + per-row order given) derive what fast_jaccard consumes
+    (`queries`: only the posting lists these query rows touch are built - the others stay empty; for parity samples
+    over very large truth sets, where sorting every posting would take minutes):
       sums       f32 sequential sum per truth row in the given order          (match_maker.py:172-174)
       post_ptr/post_rows  per column ascending truth rows, zero weights dropped (lil semantics, :122-133)
       qs_ptr/qs_cols      per query ASCENDING column ids with w32 != 0          (:111-120)
@@ -138,10 +140,18 @@ def finish_index(enc):
     L.orc_truth_sums(ctypes.c_int64(n_truth), _p(t_ptr, ctypes.c_int64), _p(t_cols, ctypes.c_int32),
                      _p(w32, ctypes.c_float), _p(sums, ctypes.c_float))
     # postings: (col, row) sorted by col then row, dropping zero weights
-    rows = np.repeat(np.arange(n_truth, dtype=np.int64), np.diff(t_ptr))
     keep = w32[t_cols] != 0
-    cols_k, rows_k = t_cols[keep].astype(np.int64), rows[keep]
-    order = np.lexsort((rows_k, cols_k))
+    if queries is not None:
+        q_ptr_all = np.asarray(enc['q_ptr'], dtype=np.int64)
+        q_cols_all = np.asarray(enc['q_cols'])
+        needed = np.zeros(n_vocab, dtype=bool)
+        for q in np.asarray(queries, dtype=np.int64):
+            needed[q_cols_all[q_ptr_all[q]:q_ptr_all[q + 1]]] = True
+        keep &= needed[t_cols]
+    kept = np.nonzero(keep)[0]
+    cols_k = t_cols[kept].astype(np.int64)
+    rows_k = (np.searchsorted(t_ptr, kept, side='right') - 1).astype(np.int64)
+    order = np.argsort((cols_k << 32) | rows_k, kind='stable')       # by column, then by row
     post_rows = rows_k[order].astype(np.int32)
     post_ptr = np.zeros(n_vocab + 1, dtype=np.int64)
     np.cumsum(np.bincount(cols_k, minlength=n_vocab), out=post_ptr[1:])
