@@ -243,7 +243,8 @@ def workload_config(args, stats):
            'queries': args.queries, 'truth': args.truth, 'top_n': args.top_n,
            'l2': 'flushed between timed steps (256 MiB memset, untimed)',
            'layout': f'{args.n_shards} truth shard(s) (contiguous row ranges; all_gather + merge inside each group) x '
-                     f'{args.n_groups} query group(s)'}
+                     f'{args.n_groups} query group(s)',
+           'shared_thresholds': bool(args.n_shards > 1 and not getattr(args, 'no_share_thresholds', False))}
     cfg.update(stats)
     return cfg
 
@@ -395,7 +396,8 @@ def run_ours(args):
     h_rows = torch.empty((n_q, k), dtype=torch.int64).pin_memory()
     h_count = torch.empty((n_q,), dtype=torch.int32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
-    shard = sharded.GpuShard(index, my_q_ptr, my_q_cols) if n_shards > 1 else None
+    share = n_shards > 1 and not args.no_share_thresholds
+    shard = sharded.GpuShard(index, my_q_ptr, my_q_cols, group=subgroup, share_thresholds=share) if n_shards > 1 else None
     phase_ms = {} if os.environ.get('DS_PHASE_TIMING') else None
 
     def step_device():
@@ -406,7 +408,7 @@ def run_ours(args):
 
     def step_e2e():
         if n_shards > 1:
-            sh = sharded.GpuShard(index, h_q_ptr, h_q_cols)                       # H2D of the queries
+            sh = sharded.GpuShard(index, h_q_ptr, h_q_cols, group=subgroup, share_thresholds=share)   # H2D of the queries
             rows, count, _ = sharded.sharded_topn(sh, k, group=subgroup)
             h_rows.copy_(rows, non_blocking=True)                                 # D2H of the result
             h_count.copy_(count, non_blocking=True)
@@ -731,6 +733,7 @@ def main():
     parser.add_argument('--truth-shards', type=int, default=0,
                         help='ranks the truth rows are sharded over (0 = auto: 2 when N >= 2); queries are split over N / T groups')
     parser.add_argument('--device-encode', action='store_true', help='build the index with the GPU encoder also at N=1')
+    parser.add_argument('--no-share-thresholds', action='store_true', help='truth shards prune with their local thresholds only (A/B)')
     parser.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline / parity sample (profiling runs)')
     parser.add_argument('--no-extra', action='store_true', help='skip the secondary workloads of the N = 1 record')
     parser.add_argument('--port-only', action='store_true', help='--impl reference: time the C port even when the reference is staged')

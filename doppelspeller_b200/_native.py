@@ -26,7 +26,7 @@ MAX_TITLE = 255
 EXPORTED_SYMBOLS = (
     'ds_version', 'ds_last_error', 'ds_kernel_launches', 'ds_trim', 'ds_profile_begin', 'ds_profile_end', 'ds_profile_end_split', 'ds_transform_titles',
     'ds_index_create', 'ds_index_destroy', 'ds_index_get_sums',
-    'ds_topn', 'ds_topn_retained', 'ds_topn_local', 'ds_topn_merge', 'ds_topn_rescan',
+    'ds_topn', 'ds_topn_retained', 'ds_topn_local', 'ds_topn_local_shared', 'ds_topn_merge', 'ds_topn_rescan',
     'ds_indel_ratio_u8', 'ds_indel_ratio_pairs', 'ds_levenshtein_ratio_pairs',
     'ds_construct_features', 'ds_construct_features_pairs',
     'ds_encode_max_vocab', 'ds_encode_trigrams', 'ds_gbdt_predict',
@@ -64,6 +64,7 @@ lib.ds_index_destroy.argtypes = [_vp]
 lib.ds_index_get_sums.argtypes = [_vp, _vp, _vp]
 lib.ds_topn.argtypes = [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]
 lib.ds_topn_local.argtypes = [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]
+lib.ds_topn_local_shared.argtypes = [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, ctypes.POINTER(_vp), _i32, _vp]
 lib.ds_topn_merge.argtypes = [_i32, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp]
 lib.ds_topn_rescan.argtypes = [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]
 lib.ds_indel_ratio_u8.argtypes = [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp]

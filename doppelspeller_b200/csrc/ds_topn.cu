@@ -1011,6 +1011,12 @@ struct SelectParams {
     int *state;
     int *overflow_count;
     int max_items;      // smem capacity per warp
+    // Thresholds shared between the shards of one truth DB (MODE_SCORE): every shard publishes, per query, the best lower
+    // bound of the GLOBAL k-th best score it knows (its own k-th best so far, or a peer's) and reads its peers' over
+    // NVLink peer memory.  The k-th best of any subset of the rows is a valid bound, stale values only prune less.
+    double *theta_own;                       // [n_q] call level, nullable
+    const double *theta_peers[DS_MAX_PEERS]; // the same array of the other shards (peer-mapped device pointers)
+    int n_peers;
     // candidates of k_post carry no score: it is computed here, in the reference's own float32 order
     int rescore;
     const chunk_t *chunks;
@@ -1091,7 +1097,21 @@ __global__ void __launch_bounds__(128) k_select(SelectParams p) {
     const bool by_row = p.mode == MODE_ROW;
     const int64_t q = p.batch_q[b];
     const double mx = p.q_mx[q];
-    const double theta = by_row ? p.threshold[q] : p.theta[b];
+    double theta = by_row ? p.threshold[q] : p.theta[b];
+    if (!by_row && p.n_peers > 0) {
+        double ext = 0.0;
+        if (lane < p.n_peers) ext = *reinterpret_cast<const volatile double *>(p.theta_peers[lane] + q);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) ext = fmax(ext, __shfl_xor_sync(0xffffffffu, ext, d));
+        if (ext > theta) {   // a peer knows a better bound: prune with it from now on
+            theta = ext;
+            if (lane == 0) {
+                p.theta[b] = ext;
+                p.ab[b] = filter_from_threshold(ext, mx);
+                p.theta_own[q] = ext;
+            }
+        }
+    }
     int n = 0;
     if (p.dense != nullptr) {
         for (int i0 = 0; i0 < p.dense_rows; i0 += 32) {
@@ -1243,8 +1263,10 @@ __global__ void __launch_bounds__(128) k_select(SelectParams p) {
         if (p.dense == nullptr) p.cand_count[b] = 0;
         if (!by_row && total >= p.k) {
             double th = threshold_from_key(__double2float_rn(s_kth[warp]));
+            if (!(th > theta)) th = theta;   // never below a bound already in use (a peer's)
             p.theta[b] = th;
             p.ab[b] = filter_from_threshold(th, mx);
+            if (p.theta_own != nullptr) p.theta_own[q] = th;
         }
     }
 }
@@ -1617,6 +1639,12 @@ static int launch_select(cudaStream_t stream, SelectParams sp) {
 // `fixed` = bounded-memory form: dense chunks of FIXED_ROWS rows only (cannot overflow).  Otherwise the
 // first chunk (MODE_SCORE) is dense to seed the thresholds and the rest goes through the candidate
 // buffers; queries whose buffer overflows are returned in `overflowed` to be redone with `fixed`.
+struct SharedTheta {
+    double *own = nullptr;
+    const double *peers[DS_MAX_PEERS] = {nullptr};
+    int n_peers = 0;
+};
+
 struct PipelineOut {
     double *score = nullptr;      // MODE_SCORE [n_q * m]
     int64_t *row = nullptr;       // MODE_SCORE [n_q * m]
@@ -1626,7 +1654,7 @@ struct PipelineOut {
 
 static int run_pipeline(Workspace &call_ws, const Index &ix, const QuerySet &qs, const std::vector<int32_t> &batch, int mode,
                         int k, int m, bool fixed, bool wide, const double *d_threshold, const PipelineOut &out,
-                        std::vector<int32_t> *overflowed) {
+                        std::vector<int32_t> *overflowed, const SharedTheta &shared = SharedTheta()) {
     cudaStream_t stream = call_ws.stream();
     const int n_batch = (int)batch.size();
     if (n_batch == 0) return DS_OK;
@@ -1723,6 +1751,9 @@ static int run_pipeline(Workspace &call_ws, const Index &ix, const QuerySet &qs,
     sel.n_vocab = ix.n_vocab;
     sel.q_sorted = qs.d_sorted;
     sel.q_ptr = qs.d_ptr;
+    sel.theta_own = mode == MODE_SCORE ? shared.own : nullptr;
+    sel.n_peers = mode == MODE_SCORE && shared.own != nullptr ? shared.n_peers : 0;
+    for (int i = 0; i < DS_MAX_PEERS; ++i) sel.theta_peers[i] = shared.peers[i];
 
     const int64_t n = ix.n_truth;
     int64_t r0 = 0;
@@ -1787,12 +1818,12 @@ static int run_pipeline(Workspace &call_ws, const Index &ix, const QuerySet &qs,
 // runs `ids` through the pipeline in workspace-sized batches, then redoes the overflowed ones with wide buffers and
 // what still overflows in the bounded-memory form (adversarial row order, massive ties, thresholds <= 0)
 static int run_batches(Workspace &ws, const Index &ix, const QuerySet &qs, const std::vector<int32_t> &ids, int mode, int k, int m,
-                       const double *d_threshold, const PipelineOut &out) {
+                       const double *d_threshold, const PipelineOut &out, const SharedTheta &shared = SharedTheta()) {
     std::vector<int32_t> overflowed, still_overflowed;
     for (size_t i0 = 0; i0 < ids.size(); i0 += QUERY_BATCH) {
         size_t i1 = std::min(ids.size(), i0 + QUERY_BATCH);
         std::vector<int32_t> batch(ids.begin() + i0, ids.begin() + i1);
-        DS_CHECK(run_pipeline(ws, ix, qs, batch, mode, k, m, false, false, d_threshold, out, &overflowed));
+        DS_CHECK(run_pipeline(ws, ix, qs, batch, mode, k, m, false, false, d_threshold, out, &overflowed, shared));
     }
     // second try with 4,096-entry buffers (thousands of rows tied at the threshold, e.g. a title the truth DB repeats)
     const bool wide_fits = (size_t)4 * (CAND_CAP_WIDE + m) * 12 + (size_t)4 * SELECT_HASH * 8 <= 227 * 1024;   // k_select's shared memory (4 warps per CTA)
@@ -1800,24 +1831,24 @@ static int run_batches(Workspace &ws, const Index &ix, const QuerySet &qs, const
     for (size_t i0 = 0; i0 < overflowed.size(); i0 += QUERY_BATCH / 8) {
         size_t i1 = std::min(overflowed.size(), i0 + QUERY_BATCH / 8);
         std::vector<int32_t> batch(overflowed.begin() + i0, overflowed.begin() + i1);
-        DS_CHECK(run_pipeline(ws, ix, qs, batch, mode, k, m, false, true, d_threshold, out, &still_overflowed));
+        DS_CHECK(run_pipeline(ws, ix, qs, batch, mode, k, m, false, true, d_threshold, out, &still_overflowed, shared));
     }
     for (size_t i0 = 0; i0 < still_overflowed.size(); i0 += QUERY_BATCH / 8) {
         size_t i1 = std::min(still_overflowed.size(), i0 + QUERY_BATCH / 8);
         std::vector<int32_t> batch(still_overflowed.begin() + i0, still_overflowed.begin() + i1);
-        DS_CHECK(run_pipeline(ws, ix, qs, batch, mode, k, m, true, false, d_threshold, out, nullptr));
+        DS_CHECK(run_pipeline(ws, ix, qs, batch, mode, k, m, true, false, d_threshold, out, nullptr, shared));
     }
     return DS_OK;
 }
 
 static int local_topn(Workspace &ws, const Index &ix, const QuerySet &qs, int k, int m, double *d_out_score,
-                      int64_t *d_out_row) {
+                      int64_t *d_out_row, const SharedTheta &shared = SharedTheta()) {
     std::vector<int32_t> ids((size_t)qs.n_q);
     for (int64_t q = 0; q < qs.n_q; ++q) ids[(size_t)q] = (int32_t)q;
     PipelineOut out;
     out.score = d_out_score;
     out.row = d_out_row;
-    return run_batches(ws, ix, qs, ids, MODE_SCORE, k, m, nullptr, out);
+    return run_batches(ws, ix, qs, ids, MODE_SCORE, k, m, nullptr, out, shared);
 }
 
 static int merge_topn(cudaStream_t stream, int n_shards, int64_t n_q, int k, int m, int64_t n_total, const double *d_score,
@@ -2173,8 +2204,16 @@ int ds_index_get_sums(const ds_index *index, float *out, void *stream_) {
     return DS_OK;
 }
 
-int ds_topn_local(ds_index *index, int64_t n_q, const int64_t *q_row_ptr, const uint16_t *q_col_ids, const double *q_mx,
-                  int32_t mx_mode, int32_t k, double *out_score, int64_t *out_row, double *out_mx, void *stream_) {
+int ds_topn_local_shared(ds_index *index, int64_t n_q, const int64_t *q_row_ptr, const uint16_t *q_col_ids, const double *q_mx,
+                         int32_t mx_mode, int32_t k, double *out_score, int64_t *out_row, double *out_mx, double *theta_own,
+                         const double *const *theta_peers, int32_t n_peers, void *stream_) {
+    if (n_peers < 0 || n_peers > DS_MAX_PEERS) return fail(DS_ERR_BAD_ARG, "n_peers %d outside 0..%d", n_peers, DS_MAX_PEERS);
+    if (n_peers > 0 && (theta_own == nullptr || theta_peers == nullptr)) return fail(DS_ERR_BAD_ARG, "theta_own / theta_peers is NULL");
+    if (theta_own != nullptr && !is_device_pointer(theta_own)) return fail(DS_ERR_BAD_ARG, "theta_own must be device memory");
+    SharedTheta shared;
+    shared.own = theta_own;
+    shared.n_peers = n_peers;
+    for (int i = 0; i < n_peers; ++i) shared.peers[i] = theta_peers[i];
     DS_CHECK(check_topn_args(index ? &index->ix : nullptr, n_q, q_row_ptr, q_col_ids, k));
     if (out_score == nullptr || out_row == nullptr) return fail(DS_ERR_BAD_ARG, "out_score / out_row is NULL");
     const Index &ix = index->ix;
@@ -2191,9 +2230,14 @@ int ds_topn_local(ds_index *index, int64_t n_q, const int64_t *q_row_ptr, const 
     DS_CHECK(ws.stage_out(&d_score, out_score, (size_t)n_q * m));
     DS_CHECK(ws.stage_out(&d_row, out_row, (size_t)n_q * m));
     DS_CHECK(ws.stage_out(&d_mx_out, out_mx, (size_t)n_q));
-    DS_CHECK(local_topn(ws, ix, qs, k, m, d_score, d_row));
+    DS_CHECK(local_topn(ws, ix, qs, k, m, d_score, d_row, shared));
     if (d_mx_out != nullptr) DS_CUDA(cudaMemcpyAsync(d_mx_out, qs.d_mx, (size_t)n_q * 8, cudaMemcpyDeviceToDevice, stream));
     return ws.finish_outputs();
+}
+
+int ds_topn_local(ds_index *index, int64_t n_q, const int64_t *q_row_ptr, const uint16_t *q_col_ids, const double *q_mx,
+                  int32_t mx_mode, int32_t k, double *out_score, int64_t *out_row, double *out_mx, void *stream_) {
+    return ds_topn_local_shared(index, n_q, q_row_ptr, q_col_ids, q_mx, mx_mode, k, out_score, out_row, out_mx, nullptr, nullptr, 0, stream_);
 }
 
 int ds_topn_merge(int32_t n_shards, int64_t n_q, int32_t k, int64_t n_truth_total, const double *all_score,

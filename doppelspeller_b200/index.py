@@ -98,9 +98,11 @@ class TruthIndex:
         return rows, count
 
     # ---- sharded phases ----
-    def topn_local(self, q_row_ptr, q_col_ids, k, q_mx=None, mx_mode=nat.DS_MX_PY312_COMPENSATED):
+    def topn_local(self, q_row_ptr, q_col_ids, k, q_mx=None, mx_mode=nat.DS_MX_PY312_COMPENSATED, theta_own=None, theta_peers=()):
         """Phase 1: this shard's best m = topn_retained(k) candidates per query -> (score f64[Q,m],
-        global row int64[Q,m], mx f64[Q])."""
+        global row int64[Q,m], mx f64[Q]).  `theta_own` (float64 CUDA tensor [Q], zeroed and synchronised by the
+        caller) and `theta_peers` (peer-mapped device addresses of the other shards' arrays) share the pruning
+        thresholds between the shards while they scan (ds_topn_local_shared)."""
         self._check_queries(q_row_ptr, q_col_ids, q_mx)
         n_q = int(q_row_ptr.shape[0]) - 1
         m = nat.topn_retained(k)
@@ -109,8 +111,15 @@ class TruthIndex:
         score = _empty((n_q, m), 'float64', cuda, dev)
         row = _empty((n_q, m), 'int64', cuda, dev)
         mx = _empty((n_q,), 'float64', cuda, dev)
-        nat.check(nat.lib.ds_topn_local(self._handle, n_q, nat.ptr(q_row_ptr), nat.ptr(q_col_ids), nat.ptr(q_mx), mx_mode, k,
-                                        nat.ptr(score), nat.ptr(row), nat.ptr(mx), self._stream()))
+        if theta_own is None:
+            nat.check(nat.lib.ds_topn_local(self._handle, n_q, nat.ptr(q_row_ptr), nat.ptr(q_col_ids), nat.ptr(q_mx), mx_mode, k,
+                                            nat.ptr(score), nat.ptr(row), nat.ptr(mx), self._stream()))
+        else:
+            nat.expect(theta_own, 'float64', 'theta_own')
+            peers = (ctypes.c_void_p * max(1, len(theta_peers)))(*[int(p) for p in theta_peers])
+            nat.check(nat.lib.ds_topn_local_shared(self._handle, n_q, nat.ptr(q_row_ptr), nat.ptr(q_col_ids), nat.ptr(q_mx), mx_mode, k,
+                                                   nat.ptr(score), nat.ptr(row), nat.ptr(mx), nat.ptr(theta_own), peers,
+                                                   len(theta_peers), self._stream()))
         return score, row, mx
 
     def topn_rescan(self, q_row_ptr, q_col_ids, q_mx, threshold, flags, k, rows, count):

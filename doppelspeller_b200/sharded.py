@@ -54,13 +54,43 @@ def combine_rescans(per_shard_rows, per_shard_count, k):
     return out, filled
 
 
-class GpuShard:
-    """Kernel backend of one rank: wraps a TruthIndex, moves the replicated queries to its device once."""
+_SHARED_THETA = {}
 
-    def __init__(self, index, q_row_ptr, q_col_ids, mx_mode=nat.DS_MX_PY312_COMPENSATED):
+
+def shared_thresholds(n_q, device, group):
+    """Symmetric (NVLink peer-mapped) float64[n_q] buffer of this rank + the peers' addresses, for ds_topn_local_shared.
+    Allocated and exchanged once per (size, device, group) - the rendezvous is a collective.  None when symmetric
+    memory is not available (single rank, CPU backends, no peer access)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) < 2:
+        return None
+    key = (int(n_q), int(device.index), id(group))
+    if key not in _SHARED_THETA:
+        entry = None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            theta = symm.empty(max(1, int(n_q)), dtype=torch.float64, device=device)
+            handle = symm.rendezvous(theta, group if group is not None else dist.group.WORLD)
+            peers = [int(handle.buffer_ptrs[r]) for r in range(handle.world_size) if r != handle.rank]
+            if len(peers) <= 31:
+                entry = (theta, handle, peers)
+        except Exception as error:   # the scan then runs with local thresholds only
+            import warnings
+            warnings.warn(f'shared thresholds unavailable: {error!r}')
+        _SHARED_THETA[key] = entry
+    return _SHARED_THETA[key]
+
+
+class GpuShard:
+    """Kernel backend of one rank: wraps a TruthIndex, moves the replicated queries to its device once.
+    `group` (the ranks holding the other shards of the same truth DB) enables the shared pruning thresholds."""
+
+    def __init__(self, index, q_row_ptr, q_col_ids, mx_mode=nat.DS_MX_PY312_COMPENSATED, group=None, share_thresholds=False):
         import torch
         self.index = index
         self.device = torch.device('cuda', index.device)
+        self._shared = shared_thresholds(int(q_row_ptr.shape[0]) - 1, self.device, group) if share_thresholds else None
         if isinstance(q_row_ptr, np.ndarray):
             q_row_ptr = torch.as_tensor(np.ascontiguousarray(q_row_ptr, dtype=np.int64))
             q_col_ids = torch.as_tensor(np.ascontiguousarray(q_col_ids, dtype=np.uint16))
@@ -71,7 +101,12 @@ class GpuShard:
         self.n_total = index.n_total
 
     def local(self, k):
-        return self.index.topn_local(self.q_ptr, self.q_cols, k, mx_mode=self.mx_mode)
+        if self._shared is None:
+            return self.index.topn_local(self.q_ptr, self.q_cols, k, mx_mode=self.mx_mode)
+        theta, handle, peers = self._shared
+        theta.zero_()
+        handle.barrier()      # every shard's zeros are in place before any shard reads them (device side, this stream)
+        return self.index.topn_local(self.q_ptr, self.q_cols, k, mx_mode=self.mx_mode, theta_own=theta, theta_peers=peers)
 
     def merge(self, all_score, all_row, k, q_mx):
         from .index import topn_merge

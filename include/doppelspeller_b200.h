@@ -31,6 +31,7 @@ extern "C" {
 #define DS_N_FEATURES 66        /* feature_engineering.py:67  FEATURES_COUNT */
 #define DS_MAX_TITLE 255        /* settings.py:68  MAX_CHARACTERS_ALLOWED_IN_THE_TITLE */
 #define DS_MAX_TOP_N 1024       /* largest supported top_n */
+#define DS_MAX_PEERS 31         /* most other shards whose thresholds ds_topn_local_shared reads */
 
 typedef enum ds_status {
     DS_OK = 0,
@@ -171,6 +172,18 @@ int32_t ds_topn_retained(int32_t k);
 int ds_topn_local(ds_index *index, int64_t n_q, const int64_t *q_row_ptr, const uint16_t *q_col_ids,
                   const double *q_mx, int32_t mx_mode, int32_t k, double *out_score, int64_t *out_row,
                   double *out_mx, void *stream);
+/* ds_topn_local with the per-query thresholds shared between the shards WHILE they scan (one process per GPU, NVLink
+ * peer memory, e.g. torch.distributed._symmetric_memory): `theta_own` double[n_q] is this shard's published lower bound
+ * of the global k-th best score (zero it before the call, then synchronise the shards), `theta_peers[i]` is the
+ * peer-mapped device address of shard i's array (n_peers <= DS_MAX_PEERS).  The selection kernel raises its pruning
+ * threshold to the best bound any shard has published so far; the k-th best of any subset of the rows is a valid bound
+ * and stale values only prune less, so the shards need no further synchronisation.  Results equal ds_topn_local's in
+ * every slot the merge can use; without it a shard prunes with its own k-th best only and its late blocks cost as
+ * much as its early ones (2 shards: 0.75 -> see DESIGN.md section 5 for the measured gain). */
+int ds_topn_local_shared(ds_index *index, int64_t n_q, const int64_t *q_row_ptr, const uint16_t *q_col_ids,
+                         const double *q_mx, int32_t mx_mode, int32_t k, double *out_score, int64_t *out_row,
+                         double *out_mx, double *theta_own, const double *const *theta_peers, int32_t n_peers,
+                         void *stream);
 int ds_topn_merge(int32_t n_shards, int64_t n_q, int32_t k, int64_t n_truth_total, const double *all_score,
                   const int64_t *all_row, const double *q_mx /* nullable: out_mx of ds_topn_local */,
                   int64_t *out_rows, int32_t *out_count, float *out_kth_f32, double *out_threshold,
