@@ -1774,7 +1774,17 @@ static int run_pipeline(Workspace &call_ws, const Index &ix, const QuerySet &qs,
             if (r1 > POST_ROWS) r1 = ceil_div(r1, (int64_t)POST_ROWS) * POST_ROWS;
             r1 = std::min<int64_t>(n, r1);
         }
-        const bool inverted = !dense && ix.post != nullptr && r0 % POST_ROWS == 0 && (r0 >= POST_ROWS || mode == MODE_ROW);
+        // The first `scan_rows` rows of a MODE_SCORE sweep go through the dense k_scan, whose cost (1.33 ms per 4,096-row
+        // block and 100k queries) does not depend on the thresholds; k_post costs 0.82 ms on the first block after the seed
+        // and 0.29 ms on the last at top_n = 10, but lists far more rows per block while the thresholds settle when top_n
+        // is large.  Measured on C3: top_n = 10: 38.2 ms with 4,096 or 16,384 scanned rows, 42.3 with 65,536; top_n = 100:
+        // 100.1 ms with 4,096, 74.1 ms with 65,536.  DS_SCAN_ROWS (environment) overrides.
+        static const int64_t scan_rows_env = []() {
+            const char *env = getenv("DS_SCAN_ROWS");
+            return env ? std::max<int64_t>(POST_ROWS, ceil_div(strtoll(env, nullptr, 10), (int64_t)POST_ROWS) * POST_ROWS) : (int64_t)0;
+        }();
+        const int64_t scan_rows = scan_rows_env > 0 ? scan_rows_env : (int64_t)POST_ROWS * std::min(16, std::max(1, k / 6));
+        const bool inverted = !dense && ix.post != nullptr && r0 % POST_ROWS == 0 && (r0 >= scan_rows || mode == MODE_ROW);
         if (inverted) {
             DS_CHECK(launch_post(ix, stream, pp, (int)(r0 / POST_ROWS), (int)ceil_div(r1, (int64_t)POST_ROWS)));
         } else {
