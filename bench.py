@@ -13,9 +13,10 @@ selection rule applied, [Q, top_n] candidate rows produced.
 `value`   whole-job titles/s with the query CSR already resident in HBM (device-timed, CUDA events, max over ranks);
 `e2e`     the same through the public API with pinned HOST buffers (H2D of the queries and D2H of the candidate rows
           inside the timed region).
-N > 1     (torchrun) 2-D layout: T truth shards (local scan -> all_gather -> merge, doppelspeller_b200/sharded.py) x
-          N / T independent query groups; total work is fixed -> "scaling": "strong".  Rank 0 checks a query sample
-          of the gathered result against the CPU oracle at every N.
+N > 1     (torchrun) 2-D layout: T truth shards (local scan with thresholds shared over NVLink peer memory -> all_gather ->
+          merge, doppelspeller_b200/sharded.py) x N / T independent query groups; T = 1 for c3 (the index is 40 MB: every
+          rank holds it, the queries are split), T = N for c5, --truth-shards picks T.  Total work is fixed -> "scaling":
+          "strong".  Rank 0 checks a query sample of the gathered result against the CPU oracle at every N.
 `extra`   (N = 1) the other BASELINE configs in the same record: c3-example, C4 (100M candidate pairs through the
           InDel-ratio and the 66-feature kernels), the candidate pairs of the step, C1 / C2 (example data through the
           drop-in classes, the reference's own numba path timed beside them).
@@ -250,7 +251,10 @@ def workload_config(args, stats):
 
 
 def resolve_layout(args, world):
-    args.n_shards = args.truth_shards if args.truth_shards > 0 else min(world, 2)
+    # Truth rows are sharded no further than the data asks for: C3's index is 40 MB, so every rank holds all of it and the
+    # ranks split the QUERIES (independent units, no data-path collective); C5 (BASELINE configs[4]: "truth sharded across
+    # 2/4/8 B200 with NCCL top-n merge") shards the truth rows over all ranks.  --truth-shards T picks any T x (N / T) layout.
+    args.n_shards = args.truth_shards if args.truth_shards > 0 else (world if args.workload == 'c5' else 1)
     if world % args.n_shards != 0:
         raise SystemExit(f'--truth-shards {args.n_shards} must divide the number of ranks {world}')
     args.n_groups = world // args.n_shards
@@ -342,8 +346,6 @@ def run_ours(args):
     n_q_total, n_truth = args.queries, args.truth
     # 2-D layout: the truth rows are sharded over T ranks (exchange step: all_gather + merge inside each group of T
     # ranks) and the queries are split over G = world / T such groups (independent, no collective between groups).
-    # Default T = 2 for N >= 2: the index is sharded no further than memory asks for, but the NCCL merge path is
-    # always exercised; --truth-shards N gives the fully truth-sharded layout of BASELINE configs[4].
     resolve_layout(args, world)
     n_shards, n_groups = args.n_shards, args.n_groups
     group_id, shard_id = rank // n_shards, rank % n_shards
@@ -731,7 +733,7 @@ def main():
     parser.add_argument('--top-n', type=int, default=10)
     parser.add_argument('--cpu-sample', type=int, default=20000)
     parser.add_argument('--truth-shards', type=int, default=0,
-                        help='ranks the truth rows are sharded over (0 = auto: 2 when N >= 2); queries are split over N / T groups')
+                        help='ranks the truth rows are sharded over (0 = auto: 1 for c3, all ranks for c5); queries are split over N / T groups')
     parser.add_argument('--device-encode', action='store_true', help='build the index with the GPU encoder also at N=1')
     parser.add_argument('--no-share-thresholds', action='store_true', help='truth shards prune with their local thresholds only (A/B)')
     parser.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline / parity sample (profiling runs)')

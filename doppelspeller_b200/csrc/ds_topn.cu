@@ -950,13 +950,14 @@ __global__ void __launch_bounds__(POST_WARPS * 32, POST_CTAS) k_post(PostParams 
                 }
                 acc4[idx] = make_uint4(kept[0], kept[1], kept[2], kept[3]);
                 const int mine = __popc(marks);
-                int before = 0, total = 0;
-                for (unsigned holders = __ballot_sync(0xffffffffu, marks != 0); holders != 0; holders &= holders - 1) {
-                    const int src = __ffs(holders) - 1;
-                    const int count = __shfl_sync(0xffffffffu, mine, src);
-                    if (src < lane) before += count;
-                    total += count;
+                int incl = mine;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int up = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += up;
                 }
+                const int before = incl - mine;
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
                 // the list holds POST_LIST rows; 256 candidates at once only happen with a negative bar
                 for (int first = 0; first < total; first += POST_LIST) {
                     if (n_list > 0 && n_list + min(total - first, POST_LIST) > POST_LIST) {
