@@ -27,9 +27,9 @@ EXPORTED_SYMBOLS = (
     'ds_version', 'ds_last_error', 'ds_kernel_launches', 'ds_trim', 'ds_profile_begin', 'ds_profile_end', 'ds_profile_end_split', 'ds_transform_titles',
     'ds_index_create', 'ds_index_destroy', 'ds_index_get_sums',
     'ds_topn', 'ds_topn_retained', 'ds_topn_local', 'ds_topn_local_shared', 'ds_topn_merge', 'ds_topn_rescan',
-    'ds_indel_ratio_u8', 'ds_indel_ratio_pairs', 'ds_levenshtein_ratio_pairs',
+    'ds_indel_ratio_u8', 'ds_indel_ratio_pairs', 'ds_levenshtein_ratio_pairs', 'ds_prematch_pairs', 'ds_select_close_matches',
     'ds_construct_features', 'ds_construct_features_pairs',
-    'ds_encode_max_vocab', 'ds_encode_trigrams', 'ds_gbdt_predict',
+    'ds_encode_max_vocab', 'ds_encode_trigrams', 'ds_title_features', 'ds_gbdt_predict',
 )
 
 
@@ -57,6 +57,7 @@ lib.ds_topn_retained.argtypes = [_i32]
 lib.ds_encode_max_vocab.restype = _i32
 lib.ds_encode_trigrams.argtypes = [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_i32),
                                    ctypes.POINTER(_i64), ctypes.POINTER(_i64), ctypes.c_int, _vp]
+lib.ds_title_features.argtypes = [_vp, _vp, _i64, _vp, _vp, ctypes.c_int, _vp]
 lib.ds_transform_titles.argtypes = [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, ctypes.c_int, _vp]
 lib.ds_gbdt_predict.argtypes = [_vp, _i64, _i32, _vp, _vp, _i32, ctypes.c_float, _i32, _vp, _vp]
 lib.ds_index_create.argtypes = [ctypes.POINTER(_vp), ctypes.c_int, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _i64, _vp]
@@ -70,6 +71,8 @@ lib.ds_topn_rescan.argtypes = [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _v
 lib.ds_indel_ratio_u8.argtypes = [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp]
 lib.ds_indel_ratio_pairs.argtypes = [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp]
 lib.ds_levenshtein_ratio_pairs.argtypes = [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp]
+lib.ds_prematch_pairs.argtypes = [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i32, _vp, _vp]
+lib.ds_select_close_matches.argtypes = [_vp, _vp, _i64, _i32, _i32, _vp, _vp]
 lib.ds_construct_features.argtypes = [_vp, _vp, _vp, _vp, _i64, _vp, _u8, _u32, _i64, _vp, _vp]
 lib.ds_construct_features_pairs.argtypes = [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _u8, _u32, _i64, _vp, _vp]
 for _name in EXPORTED_SYMBOLS:

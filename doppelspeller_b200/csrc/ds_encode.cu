@@ -11,6 +11,8 @@
 // c0 * 37^2 + c1 * 37 + c2 over the alphabet ' a..z0..9'), the order `encode.encode_canonical` defines on
 // the host and every benchmark uses.  `MatchMaker.__init__` keeps the reference's own order for bit-parity
 // with one particular reference process.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_reduce.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
@@ -194,6 +196,88 @@ __global__ void k_transform(const uint32_t *__restrict__ cps, const int64_t *__r
 
 using namespace ds;
 
+// ---------------------------------------------------------------------------------------------------
+// f3: the pair kernels' per-title inputs from the transformed-title table, on the device
+//   FeatureEngineering.encode_title            feature_engineering.py:298-307  (38-symbol codes)
+//   common.get_words_counter                   common.py:140-142               (document frequency over per-title word SETS)
+//   FeatureEngineering.get_truth_words_counts  feature_engineering.py:309-319  (df of each of a title's first 15 words)
+// Words are the tokens of str.split(): runs of non-white-space bytes.  A word is identified by its 64-bit FNV-1a hash
+// (1.7M words at 500k titles: collision probability ~1e-7); every (title, word) pair counts once, like the set does.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool is_space_byte(uint8_t c) { return c == ' ' || (c >= 9 && c <= 13) || (c >= 0x1c && c <= 0x1f); }
+
+// PASS 0: number of words of every title.  PASS 1: hash of every word, whether it is the first occurrence inside its
+// title, and the hashes of the title's first DS_N_WORDS words.
+template <int PASS>
+__global__ void k_words(const uint8_t *__restrict__ bytes, const int64_t *__restrict__ offsets, int64_t n_titles, int64_t *__restrict__ n_words,
+                        const int64_t *__restrict__ word_ptr, unsigned long long *__restrict__ keys, uint32_t *__restrict__ first_in_title,
+                        unsigned long long *__restrict__ head) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_titles) return;
+    const uint8_t *p = bytes + offsets[t];
+    const int len = (int)(offsets[t + 1] - offsets[t]);
+    int64_t at = PASS == 1 ? word_ptr[t] : 0;
+    const int64_t first = at;
+    int count = 0;
+    int i = 0;
+    while (i < len) {
+        while (i < len && is_space_byte(p[i])) ++i;
+        if (i >= len) break;
+        unsigned long long h = 14695981039346656037ull;
+        while (i < len && !is_space_byte(p[i])) {
+            h = (h ^ p[i]) * 1099511628211ull;
+            ++i;
+        }
+        if (PASS == 1) {
+            bool seen = false;
+            for (int64_t j = first; j < at; ++j) seen |= keys[j] == h;
+            keys[at] = h;
+            first_in_title[at] = seen ? 0u : 1u;
+            if (count < DS_N_WORDS) head[t * DS_N_WORDS + count] = h;
+            ++at;
+        }
+        ++count;
+    }
+    if (PASS == 0) n_words[t] = count;
+    else
+        for (int c = count; c < DS_N_WORDS; ++c) head[t * DS_N_WORDS + c] = 0ull;
+}
+
+// counts[t][slot] = document frequency of the title's slot-th word (binary search among the distinct hashes), 0 past its words
+__global__ void k_word_lookup(const unsigned long long *__restrict__ head, const int64_t *__restrict__ n_words, int64_t n_titles,
+                              const unsigned long long *__restrict__ distinct, const uint32_t *__restrict__ df, const int *__restrict__ n_distinct,
+                              uint32_t *__restrict__ counts) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_titles * DS_N_WORDS) return;
+    const int64_t t = i / DS_N_WORDS;
+    const int slot = (int)(i % DS_N_WORDS);
+    uint32_t value = 0;
+    if (slot < n_words[t]) {
+        const unsigned long long h = head[i];
+        int lo = 0, hi = *n_distinct;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (distinct[mid] < h) lo = mid + 1;
+            else hi = mid;
+        }
+        value = df[lo];
+    }
+    counts[i] = value;
+}
+
+__global__ void k_title_codes(const uint8_t *__restrict__ bytes, int64_t n, uint8_t *__restrict__ codes, int *__restrict__ bad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t c = bytes[i];
+    uint8_t code = 255;
+    if (c >= 'a' && c <= 'z') code = (uint8_t)(c - 'a' + 2);
+    else if (c >= '0' && c <= '9') code = (uint8_t)(c - '0' + 28);
+    else if (c == ' ') code = 1;
+    else if (c == '-') code = 0;
+    if (code == 255) atomicOr(bad, 1);
+    codes[i] = code;
+}
+
 extern "C" {
 
 int32_t ds_encode_max_vocab(void) { return ENC_CODES; }
@@ -368,6 +452,92 @@ int ds_transform_titles(const uint32_t *codepoints, const int64_t *offsets, int6
         k_transform<1><<<(unsigned)ceil_div(n_titles, 128), 128, 0, stream>>>(d_cps, d_off, n_titles, d_table, table_len, d_raw, nullptr,
                                                                             d_out_off, d_out);
         DS_LAUNCHED("k_transform");
+    }
+    return ws.finish_outputs();
+}
+
+int ds_title_features(const uint8_t *bytes, const int64_t *offsets, int64_t n_titles, uint8_t *out_codes, uint32_t *out_word_counts,
+                      int device, void *stream_) {
+    if (n_titles < 0) return fail(DS_ERR_BAD_ARG, "n_titles < 0");
+    if (n_titles == 0) return DS_OK;
+    if (!bytes || !offsets) return fail(DS_ERR_BAD_ARG, "NULL argument");
+    int n_devices = 0;
+    if (cudaGetDeviceCount(&n_devices) != cudaSuccess || n_devices == 0) {
+        cudaGetLastError();
+        return fail(DS_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    DeviceGuard guard(device);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    Workspace ws(stream);
+    int64_t total = 0;
+    if (is_device_pointer(offsets)) {
+        DS_CUDA(cudaMemcpyAsync(&total, offsets + n_titles, 8, cudaMemcpyDeviceToHost, stream));
+        DS_CUDA(cudaStreamSynchronize(stream));
+    } else {
+        total = offsets[n_titles];
+    }
+    const uint8_t *d_bytes = nullptr;
+    const int64_t *d_offsets = nullptr;
+    DS_CHECK(ws.stage_in(&d_bytes, bytes, (size_t)std::max<int64_t>(1, total)));
+    DS_CHECK(ws.stage_in(&d_offsets, offsets, (size_t)n_titles + 1));
+    if (out_codes != nullptr && total > 0) {
+        uint8_t *d_codes = nullptr;
+        int *d_bad = nullptr;
+        DS_CHECK(ws.stage_out(&d_codes, out_codes, (size_t)total));
+        DS_CHECK(ws.alloc(&d_bad, 1));
+        DS_CUDA(cudaMemsetAsync(d_bad, 0, 4, stream));
+        k_title_codes<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(d_bytes, total, d_codes, d_bad);
+        DS_LAUNCHED("k_title_codes");
+        int h_bad = 0;
+        DS_CUDA(cudaMemcpyAsync(&h_bad, d_bad, 4, cudaMemcpyDeviceToHost, stream));
+        DS_CUDA(cudaStreamSynchronize(stream));
+        if (h_bad) return fail(DS_ERR_BAD_ARG, "a title holds a character outside '- a-z0-9' (encode_title would fail on it)");
+    }
+    if (out_word_counts != nullptr) {
+        int64_t *d_n_words = nullptr, *d_word_ptr = nullptr;
+        DS_CHECK(ws.alloc(&d_n_words, (size_t)n_titles + 1));
+        DS_CHECK(ws.alloc(&d_word_ptr, (size_t)n_titles + 1));
+        DS_CUDA(cudaMemsetAsync(d_n_words, 0, ((size_t)n_titles + 1) * 8, stream));
+        const unsigned blocks = (unsigned)ceil_div(n_titles, 128);
+        k_words<0><<<blocks, 128, 0, stream>>>(d_bytes, d_offsets, n_titles, d_n_words, nullptr, nullptr, nullptr, nullptr);
+        DS_LAUNCHED("k_words");
+        DS_CHECK(exclusive_sum_i64(ws, d_n_words, d_word_ptr, n_titles + 1));
+        int64_t n_words = 0;
+        DS_CUDA(cudaMemcpyAsync(&n_words, d_word_ptr + n_titles, 8, cudaMemcpyDeviceToHost, stream));
+        DS_CUDA(cudaStreamSynchronize(stream));
+        if (n_words > INT32_MAX) return fail(DS_ERR_UNSUPPORTED, "more than 2^31-1 words");
+        unsigned long long *d_keys = nullptr, *d_keys_sorted = nullptr, *d_head = nullptr, *d_distinct = nullptr;
+        uint32_t *d_first = nullptr, *d_first_sorted = nullptr, *d_df = nullptr, *d_counts = nullptr;
+        int *d_n_distinct = nullptr;
+        const size_t words_alloc = (size_t)std::max<int64_t>(1, n_words);
+        DS_CHECK(ws.alloc(&d_keys, words_alloc));
+        DS_CHECK(ws.alloc(&d_keys_sorted, words_alloc));
+        DS_CHECK(ws.alloc(&d_first, words_alloc));
+        DS_CHECK(ws.alloc(&d_first_sorted, words_alloc));
+        DS_CHECK(ws.alloc(&d_distinct, words_alloc + 1));
+        DS_CHECK(ws.alloc(&d_df, words_alloc + 1));
+        DS_CHECK(ws.alloc(&d_n_distinct, 1));
+        DS_CHECK(ws.alloc(&d_head, (size_t)n_titles * DS_N_WORDS));
+        DS_CHECK(ws.stage_out(&d_counts, out_word_counts, (size_t)n_titles * DS_N_WORDS));
+        DS_CUDA(cudaMemsetAsync(d_n_distinct, 0, 4, stream));
+        DS_CUDA(cudaMemsetAsync(d_df, 0, (words_alloc + 1) * 4, stream));
+        k_words<1><<<blocks, 128, 0, stream>>>(d_bytes, d_offsets, n_titles, nullptr, d_word_ptr, d_keys, d_first, d_head);
+        DS_LAUNCHED("k_words");
+        if (n_words > 0) {
+            size_t sort_bytes = 0, reduce_bytes = 0;
+            DS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, d_keys, d_keys_sorted, d_first, d_first_sorted, (int)n_words, 0, 64, stream));
+            DS_CUDA(cub::DeviceReduce::ReduceByKey(nullptr, reduce_bytes, d_keys_sorted, d_distinct, d_first_sorted, d_df, d_n_distinct,
+                                                   ::cuda::std::plus<>(), (int)n_words, stream));
+            unsigned char *d_temp = nullptr;
+            DS_CHECK(ws.alloc(&d_temp, std::max(sort_bytes, reduce_bytes)));
+            DS_CUDA(cub::DeviceRadixSort::SortPairs(d_temp, sort_bytes, d_keys, d_keys_sorted, d_first, d_first_sorted, (int)n_words, 0, 64, stream));
+            DS_CUDA(cub::DeviceReduce::ReduceByKey(d_temp, reduce_bytes, d_keys_sorted, d_distinct, d_first_sorted, d_df, d_n_distinct,
+                                                   ::cuda::std::plus<>(), (int)n_words, stream));
+            g_kernel_launches.fetch_add(2);
+        }
+        k_word_lookup<<<(unsigned)ceil_div(n_titles * DS_N_WORDS, 256), 256, 0, stream>>>(d_head, d_n_words, n_titles, d_distinct, d_df,
+                                                                                          d_n_distinct, d_counts);
+        DS_LAUNCHED("k_word_lookup");
     }
     return ws.finish_outputs();
 }

@@ -754,6 +754,74 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k_feature_words(PairSource src,
 }
 
 // ---------------------------------------------------------------------------------------------------
+// f2: the fuzzy pre-match of Prediction (predict.py:140-183) on the device.
+//   k_prematch_filter   _get_levenshtein_deletion_ratio (:140-145) in float64, the written association: pairs below the
+//                       threshold get 0 (:150-151), the others are listed for the ratio kernel
+//   k_prematch_again    pairs whose levenshtein_ratio is <= threshold are listed for the token-sorted ratio (:154-155)
+//   k_select_close      per test title: the candidate with ratio > threshold that alone attains the title's maximum
+//                       (:172-176 keep `> 94`, groupby-max, drop titles whose maximum is attained twice)
+// The list lengths stay on the device (the ratio kernels read them there): no host synchronisation in the cascade.
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_prematch_filter(PairSource src, int64_t n, double threshold, int32_t *__restrict__ out, int32_t *__restrict__ list,
+                                  int *__restrict__ count) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool keep = false;
+    if (p < n) {
+        const int la = side_length(src.a, p), lb = side_length(src.b, p);
+        const double total = (double)(la + lb), delta = (double)abs(la - lb);
+        const double deletion = __dmul_rn(__ddiv_rn(__dsub_rn(total, delta), total), 100.0);   // 0 / 0 = NaN: not < threshold
+        keep = !(deletion < threshold);
+        if (!keep) out[p] = 0;
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0 && ballot != 0) base = atomicAdd(count, __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (keep) list[base + __popc(ballot & ((1u << lane) - 1))] = (int32_t)p;
+}
+
+__global__ void k_prematch_again(const int32_t *__restrict__ list, const int *__restrict__ count, const int32_t *__restrict__ out,
+                                 int32_t threshold, int32_t *__restrict__ list2, int *__restrict__ count2) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool again = false;
+    int32_t p = 0;
+    if (i < *count) {
+        p = list[i];
+        again = out[p] <= threshold;
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, again);
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0 && ballot != 0) base = atomicAdd(count2, __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (again) list2[base + __popc(ballot & ((1u << lane) - 1))] = p;
+}
+
+// one thread per test title over its `run` consecutive pairs; invalid[p] != 0 (nullable) excludes a pair
+__global__ void k_select_close(const int32_t *__restrict__ ratios, const uint8_t *__restrict__ invalid, int64_t n_titles, int run,
+                               int32_t threshold, int64_t *__restrict__ out_pair) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_titles) return;
+    int32_t best = threshold;
+    int64_t at = -1;
+    int times = 0;
+    for (int j = 0; j < run; ++j) {
+        const int64_t p = q * run + j;
+        if (invalid != nullptr && invalid[p]) continue;
+        const int32_t r = ratios[p];
+        if (r > best) {
+            best = r;
+            at = p;
+            times = 1;
+        } else if (r == best && at >= 0) {
+            ++times;
+        }
+    }
+    out_pair[q] = times == 1 ? at : -1;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
 template <typename W, int MAXLEN, int BLOCK, int MODE>
@@ -1043,6 +1111,73 @@ int ds_construct_features_pairs(const uint8_t *bytes_a, const int64_t *offsets_a
     float *d_out = nullptr;
     DS_CHECK(ws.stage_out(&d_out, out, (size_t)n_pairs * DS_N_FEATURES));
     DS_CHECK(launch_features(ws, src, d_counts, 0, space_code, n_truth, n_pairs, d_out));
+    return ws.finish_outputs();
+}
+
+int ds_prematch_pairs(const uint8_t *bytes_a, const int64_t *offsets_a, const uint8_t *sorted_a, const int64_t *sorted_offsets_a,
+                      int64_t n_titles_a, const uint8_t *bytes_b, const int64_t *offsets_b, const uint8_t *sorted_b,
+                      const int64_t *sorted_offsets_b, int64_t n_titles_b, const int32_t *idx_a, const int32_t *idx_b, int64_t n,
+                      int32_t threshold, int32_t *out_ratio, void *stream_) {
+    if (n < 0) return fail(DS_ERR_BAD_ARG, "n < 0");
+    if (n == 0) return DS_OK;
+    if (!bytes_a || !offsets_a || !sorted_a || !sorted_offsets_a || !bytes_b || !offsets_b || !sorted_b || !sorted_offsets_b || !idx_a ||
+        !idx_b || !out_ratio)
+        return fail(DS_ERR_BAD_ARG, "NULL argument");
+    if (n > INT32_MAX) return fail(DS_ERR_UNSUPPORTED, "more than 2^31-1 pairs per call");
+    DS_CHECK(require_device());
+    DeviceGuard guard(owning_device({bytes_a, bytes_b, sorted_a, sorted_b, offsets_a, offsets_b, idx_a, idx_b, out_ratio}));
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    Workspace ws(stream);
+    PairSource raw, sorted;
+    DS_CHECK(stage_table(ws, bytes_a, offsets_a, n_titles_a, idx_a, n, &raw.a));
+    DS_CHECK(stage_table(ws, bytes_b, offsets_b, n_titles_b, idx_b, n, &raw.b));
+    sorted.a = raw.a;
+    sorted.b = raw.b;
+    DS_CHECK(ws.stage_in(&sorted.a.off, sorted_offsets_a, (size_t)n_titles_a + 1));
+    DS_CHECK(ws.stage_in(&sorted.b.off, sorted_offsets_b, (size_t)n_titles_b + 1));
+    if (is_device_pointer(sorted_a)) sorted.a.base = sorted_a;
+    else DS_CHECK(ws.stage_in(&sorted.a.base, sorted_a, (size_t)std::max<int64_t>(1, sorted_offsets_a[n_titles_a])));
+    if (is_device_pointer(sorted_b)) sorted.b.base = sorted_b;
+    else DS_CHECK(ws.stage_in(&sorted.b.base, sorted_b, (size_t)std::max<int64_t>(1, sorted_offsets_b[n_titles_b])));
+    K2Out out{};
+    DS_CHECK(ws.stage_out(&out.i32, out_ratio, (size_t)n));
+    int32_t *d_list = nullptr, *d_list2 = nullptr;
+    int *d_count = nullptr;   // [0] pairs past the length filter, [1] pairs that need the token-sorted ratio
+    DS_CHECK(ws.alloc(&d_list, (size_t)n));
+    DS_CHECK(ws.alloc(&d_list2, (size_t)n));
+    DS_CHECK(ws.alloc(&d_count, 2));
+    DS_CUDA(cudaMemsetAsync(d_count, 0, 8, stream));
+    const unsigned blocks = (unsigned)ceil_div(n, 256);
+    k_prematch_filter<<<blocks, 256, 0, stream>>>(raw, n, (double)threshold, out.i32, d_list, d_count);
+    DS_LAUNCHED("k_prematch_filter");
+    const size_t smem = sizeof(K2Smem<u64, 255, 64>);
+    DS_CHECK((ensure_dynamic_smem(reinterpret_cast<const void *>(&k_indel_pairs<u64, 255, 64, 1>), smem)));
+    k_indel_pairs<u64, 255, 64, 1><<<(unsigned)ceil_div(n, 64), 64, smem, stream>>>(raw, d_list, n, out, d_count);
+    DS_LAUNCHED("k_indel_pairs");
+    k_prematch_again<<<blocks, 256, 0, stream>>>(d_list, d_count, out.i32, threshold, d_list2, d_count + 1);
+    DS_LAUNCHED("k_prematch_again");
+    k_indel_pairs<u64, 255, 64, 1><<<(unsigned)ceil_div(n, 64), 64, smem, stream>>>(sorted, d_list2, n, out, d_count + 1);
+    DS_LAUNCHED("k_indel_pairs");
+    return ws.finish_outputs();
+}
+
+int ds_select_close_matches(const int32_t *ratios, const uint8_t *invalid, int64_t n_titles, int32_t run, int32_t threshold,
+                            int64_t *out_pair, void *stream_) {
+    if (n_titles < 0 || run < 1) return fail(DS_ERR_BAD_ARG, "n_titles < 0 or run < 1");
+    if (n_titles == 0) return DS_OK;
+    if (!ratios || !out_pair) return fail(DS_ERR_BAD_ARG, "NULL argument");
+    DS_CHECK(require_device());
+    DeviceGuard guard(owning_device({ratios, invalid, out_pair}));
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    Workspace ws(stream);
+    const int32_t *d_ratios = nullptr;
+    const uint8_t *d_invalid = nullptr;
+    int64_t *d_out = nullptr;
+    DS_CHECK(ws.stage_in(&d_ratios, ratios, (size_t)n_titles * run));
+    DS_CHECK(ws.stage_in(&d_invalid, invalid, (size_t)n_titles * run));
+    DS_CHECK(ws.stage_out(&d_out, out_pair, (size_t)n_titles));
+    k_select_close<<<(unsigned)ceil_div(n_titles, 256), 256, 0, stream>>>(d_ratios, d_invalid, n_titles, run, threshold, d_out);
+    DS_LAUNCHED("k_select_close");
     return ws.finish_outputs();
 }
 

@@ -1597,8 +1597,13 @@ static int launch_post(const Index &ix, cudaStream_t stream, PostParams pp, int 
     const long long wanted_tasks = (long long)148 * 2 * POST_WARPS * 2;
     pp.run_len = (int)std::min<long long>(POST_RUN, std::max<long long>(1, (long long)(s1 - s0) * pp.n_batch / wanted_tasks));
     pp.n_tasks = ceil_div(s1 - s0, pp.run_len) * (long long)pp.n_batch;
-    // tasks are handed out warp by warp inside a CTA; DS_POST_TASKS per warp level the very uneven task lengths
-    pp.tasks_per_cta = (int)std::min<long long>(POST_WARPS * DS_POST_TASKS, std::max<long long>(POST_WARPS, ceil_div(pp.n_tasks, (long long)148 * 2 * 2)));
+    // Tasks are handed out warp by warp inside a CTA (up to DS_POST_TASKS per warp level the very uneven task lengths);
+    // the grid is a whole number of waves of 148 SMs x 2 resident CTAs, so that a small launch (a few thousand
+    // queries per rank at 8 GPUs) is one full wave instead of one full and one nearly empty one.
+    const long long resident = (long long)148 * POST_CTAS;
+    const long long most_per_cta = (long long)POST_WARPS * DS_POST_TASKS;
+    const long long waves = std::max<long long>(1, ceil_div(pp.n_tasks, resident * most_per_cta));
+    pp.tasks_per_cta = (int)std::max<long long>(1, ceil_div(pp.n_tasks, resident * waves));
     const long long ctas = ceil_div(pp.n_tasks, (long long)pp.tasks_per_cta);
     if (ctas > INT32_MAX) return fail(DS_ERR_UNSUPPORTED, "too many posting tasks in one launch");
     const size_t smem = (size_t)POST_WARPS * (POST_ROWS * sizeof(post_acc_t) + POST_LIST * 2 + POST_DESC * 8);

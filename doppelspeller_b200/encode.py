@@ -89,10 +89,10 @@ def title_table(titles):
     return (np.array(data) if data.size else np.zeros(1, dtype=np.uint8)), offsets
 
 
-def encode_canonical_device(test_titles, truth_titles, device=0, truth_table=None):
+def encode_canonical_device(test_titles, truth_titles, device=0, truth_table=None, query_table=None):
     """`encode_canonical` on the GPU (csrc/ds_encode.cu): same outputs, as CUDA tensors that plug straight into
-    TruthIndex / MatchMaker.from_encoded without touching the host again.  `truth_table` = (bytes, offsets) CUDA
-    tensors of a truth side that is already resident (skips the host string join and the H2D copy)."""
+    TruthIndex / MatchMaker.from_encoded without touching the host again.  `truth_table` / `query_table` = (bytes,
+    offsets) CUDA tensors of a side that is already resident (skips the host string join and the H2D copy)."""
     import ctypes
 
     import torch
@@ -108,19 +108,24 @@ def encode_canonical_device(test_titles, truth_titles, device=0, truth_table=Non
         d_tb, d_to = truth_table
         truth_total = int(d_tb.shape[0])
     n_truth = int(d_to.shape[0]) - 1
-    q_bytes, q_off = title_table(test_titles)
-    d_qb, d_qo = to_dev(q_bytes), to_dev(q_off)
+    if query_table is None:
+        q_bytes, q_off = title_table(test_titles)
+        d_qb, d_qo = to_dev(q_bytes), to_dev(q_off)
+        n_queries, query_total = len(test_titles), int(q_off[-1])
+    else:
+        d_qb, d_qo = query_table
+        n_queries, query_total = int(d_qo.shape[0]) - 1, int(d_qb.shape[0])
     max_vocab = int(nat.lib.ds_encode_max_vocab())
     t_ptr = torch.empty(n_truth + 1, dtype=torch.int64, device=dev)
-    q_ptr = torch.empty(len(test_titles) + 1, dtype=torch.int64, device=dev)
+    q_ptr = torch.empty(n_queries + 1, dtype=torch.int64, device=dev)
     t_cols = torch.empty(max(1, truth_total), dtype=torch.uint16, device=dev)
-    q_cols = torch.empty(max(1, int(q_off[-1])), dtype=torch.uint16, device=dev)
+    q_cols = torch.empty(max(1, query_total), dtype=torch.uint16, device=dev)
     idf64 = torch.empty(max_vocab, dtype=torch.float64, device=dev)
     vocab = torch.empty(max_vocab, dtype=torch.int32, device=dev)
     n_vocab, t_nnz, q_nnz = ctypes.c_int32(0), ctypes.c_int64(0), ctypes.c_int64(0)
     with torch.cuda.device(dev):
         nat.check(nat.lib.ds_encode_trigrams(
-            nat.ptr(d_tb), nat.ptr(d_to), n_truth, nat.ptr(d_qb), nat.ptr(d_qo), len(test_titles), nat.ptr(t_ptr),
+            nat.ptr(d_tb), nat.ptr(d_to), n_truth, nat.ptr(d_qb), nat.ptr(d_qo), n_queries, nat.ptr(t_ptr),
             nat.ptr(t_cols), nat.ptr(q_ptr), nat.ptr(q_cols), nat.ptr(idf64), nat.ptr(vocab), ctypes.byref(n_vocab),
             ctypes.byref(t_nnz), ctypes.byref(q_nnz), device, torch.cuda.current_stream(dev).cuda_stream))
     return dict(idf64=idf64[:n_vocab.value], t_ptr=t_ptr, t_cols=t_cols[:t_nnz.value], q_ptr=q_ptr, q_cols=q_cols[:q_nnz.value],

@@ -5,8 +5,9 @@
     Prediction._get_levenshtein_ratio            predict.py:147-156
     the `> 94`, group-max and ambiguity filter   predict.py:158-176
 
-The reference maps a Python lambda over every (title, candidate) pair; here the length pre-filter is one
-vectorised numpy expression and the two ratios run as two kernel launches over the surviving pairs.
+The reference maps a Python lambda over every (title, candidate) pair.  `get_levenshtein_ratios` takes the same two
+lists of strings (host filter, two kernel calls); `get_levenshtein_ratios_indexed` + `select_close_matches_grouped` are
+the device-resident form (title tables + pair indexes in, ratios / chosen pair per title out, no host round trip).
 """
 import numpy as np
 
@@ -78,25 +79,40 @@ def _ratio_pairs(bytes_a, off_a, n_a, bytes_b, off_b, n_b, idx_a, idx_b):
 
 def get_levenshtein_ratios_indexed(tables_a, tables_b, idx_a, idx_b, threshold=LEVENSHTEIN_RATIO_THRESHOLD):
     """Prediction._get_levenshtein_ratio (predict.py:140-156) for the pairs (tables_a[idx_a[p]], tables_b[idx_b[p]]),
-    entirely on the GPU: float64 length pre-filter, levenshtein_ratio of the survivors, token-sort ratio of
-    those at or below the threshold.  idx_* are int32 CUDA tensors; returns an int32 CUDA tensor."""
+    entirely on the GPU and without a host synchronisation (ds_prematch_pairs): float64 length pre-filter,
+    levenshtein_ratio of the survivors, token-sort ratio of those at or below the threshold.  idx_* are int32 CUDA
+    tensors; returns an int32 CUDA tensor."""
     import torch
+
+    from . import _native as nat
     idx_a, idx_b = idx_a.to(torch.int32).contiguous(), idx_b.to(torch.int32).contiguous()
-    out = torch.zeros(idx_a.shape[0], dtype=torch.int32, device=idx_a.device)
-    la = tables_a.lengths[idx_a.long()].to(torch.float64)
-    lb = tables_b.lengths[idx_b.long()].to(torch.float64)
-    total = la + lb
-    deletion = ((total - (la - lb).abs()) / total) * 100                       # predict.py:140-145, float64, same association
-    keep = torch.nonzero(~(deletion < threshold)).flatten()                    # NaN (0 / 0) is not < threshold, like python
-    if keep.numel() == 0:
-        return out
-    ka, kb = idx_a[keep].contiguous(), idx_b[keep].contiguous()
-    ratios = _ratio_pairs(tables_a.raw, tables_a.raw_off, tables_a.n, tables_b.raw, tables_b.raw_off, tables_b.n, ka, kb)
-    again = torch.nonzero(ratios <= threshold).flatten()
-    if again.numel():
-        ratios[again] = _ratio_pairs(tables_a.sorted, tables_a.sorted_off, tables_a.n, tables_b.sorted, tables_b.sorted_off,
-                                     tables_b.n, ka[again].contiguous(), kb[again].contiguous())
-    out[keep] = ratios
+    n = int(idx_a.shape[0])
+    out = torch.empty(n, dtype=torch.int32, device=idx_a.device)
+    if n:
+        nat.check(nat.lib.ds_prematch_pairs(
+            nat.ptr(tables_a.raw), nat.ptr(tables_a.raw_off), nat.ptr(tables_a.sorted), nat.ptr(tables_a.sorted_off), tables_a.n,
+            nat.ptr(tables_b.raw), nat.ptr(tables_b.raw_off), nat.ptr(tables_b.sorted), nat.ptr(tables_b.sorted_off), tables_b.n,
+            nat.ptr(idx_a), nat.ptr(idx_b), n, int(threshold), nat.ptr(out), nat.stream_for(idx_a)))
+    return out
+
+
+def select_close_matches_grouped(ratios, n_titles, run, invalid=None, threshold=LEVENSHTEIN_RATIO_THRESHOLD):
+    """predict.py:158-176 for a [n_titles, run] candidate list (ds_select_close_matches): int64[n_titles], the index of
+    the pair kept as the title's "very close" match or -1.  `ratios` int32 (CUDA tensor: stays on the device; numpy:
+    staged), `invalid` optional uint8 mask of pairs to leave out."""
+    from . import _native as nat
+    cuda = hasattr(ratios, 'is_cuda') and ratios.is_cuda
+    if cuda:
+        import torch
+        out = torch.empty(n_titles, dtype=torch.int64, device=ratios.device)
+        ratios = ratios.contiguous()
+    else:
+        out = np.empty(n_titles, dtype=np.int64)
+        ratios = np.ascontiguousarray(ratios, dtype=np.int32)
+    if int(ratios.shape[0]) != n_titles * run:
+        raise ValueError('ratios must hold n_titles * run entries')
+    nat.check(nat.lib.ds_select_close_matches(nat.ptr(ratios), nat.ptr(invalid), n_titles, int(run), int(threshold), nat.ptr(out),
+                                              nat.stream_for(ratios)))
     return out
 
 

