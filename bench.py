@@ -235,6 +235,19 @@ def committed_ncu(kernel):
     return json.load(open(path))
 
 
+def measured_limiter(kernel, sources=('ds_pairs.cu', 'ds_common.cuh')):
+    """Compact form of the committed ncu summary of a secondary kernel: its busiest unit and how busy it was."""
+    ncu = committed_ncu(kernel)
+    if ncu is None:
+        return None
+    units = {'shared-memory pipe': ncu.get('smem_wavefronts_pct'), 'issue slots': ncu.get('issue_active_pct'),
+             'hbm': ncu.get('dram_throughput_pct')}
+    bound = max((name for name in units if units[name] is not None), key=lambda name: units[name])
+    return {'kernel': kernel, 'bound': bound, 'frac': units[bound] / 100.0, 'issue_active_pct': ncu.get('issue_active_pct'),
+            'smem_wavefronts_pct': ncu.get('smem_wavefronts_pct'), 'dram_throughput_pct': ncu.get('dram_throughput_pct'),
+            'source': ncu.get('source'), 'ncu_matches_current_sources': ncu.get('kernel_sources') == source_id(*sources)}
+
+
 def workload_config(args, stats):
     spec = WORKLOADS.get(args.workload, {})
     tag = spec.get('tag', 'custom size')
@@ -654,7 +667,8 @@ def pair_kernels(truth, test, rows, device):
         stop.synchronize()
         ms = start.elapsed_time(stop) / 3
         out[name] = {'pairs_per_s': n / (ms / 1e3), 'pairs': n, 'ms': ms, 'algorithmic_bytes_per_pair': bytes_per_pair,
-                     'hbm_frac': n * bytes_per_pair / (ms / 1e3) / 1e9 / hbm_peak}
+                     'hbm_frac': n * bytes_per_pair / (ms / 1e3) / 1e9 / hbm_peak,
+                     'measured_limiter': measured_limiter('k_indel_groups' if name == 'indel_ratio' else 'k_feature_words')}
     # the whole hot path as one GPU-resident pass (north_star target: "100k test titles matched, nearest-n Jaccard +
     # Levenshtein features, against 500k truth titles"): host title strings in, candidate rows + features out
     pipeline = pl.CandidatePipeline(truth, device=device.index)
@@ -711,7 +725,12 @@ def second_workload(args, device):
 def c4_pairs(device):
     """BASELINE configs[3]: 100M synthetic candidate pairs, titles up to 128 characters (bench_pairs.py)."""
     import bench_pairs
-    return bench_pairs.run(pairs=100_000_000, titles=400_000, steps=2, sample=100_000, chunk=25_000_000, device=device)
+    out = bench_pairs.run(pairs=100_000_000, titles=400_000, steps=2, sample=100_000, chunk=25_000_000, device=device)
+    # the byte convention of SURVEY.md 8(d) next to what ncu measured: both kernels are bound by instruction issue / latency
+    # (bit-parallel alignments in registers and shared memory), not by the bytes of the strings
+    out['indel_ratio']['measured_limiter'] = measured_limiter('k_indel_pairs')
+    out['construct_features']['measured_limiter'] = measured_limiter('k_feature_words')
+    return out
 
 
 def example_dropin(device):
