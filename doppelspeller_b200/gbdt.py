@@ -34,6 +34,32 @@ class GbdtModel:
         self.base_margin = float(np.float32(base_margin))
         self.transform = int(transform)
         self._device_copy = {}
+        self.n_features_needed = self._validate()
+
+    def _validate(self):
+        """Every walk must stay inside its tree and end: children inside the tree and after their parent, at most 65,535
+        nodes per tree (u16 child indexes).  Checked once on the host - the kernel walks device copies unchecked.
+        Returns 1 + the largest feature index a split uses."""
+        offsets, nodes = self.tree_offsets, self.nodes
+        if offsets.ndim != 1 or offsets.shape[0] < 1 or offsets[0] != 0 or (np.diff(offsets) < 0).any() or int(offsets[-1]) != nodes.shape[0]:
+            raise ValueError('tree_offsets must start at 0, be non-decreasing and end at len(nodes)')
+        sizes = np.diff(offsets).astype(np.int64)
+        if sizes.size and int(sizes.max()) > 65535:
+            raise ValueError(f'a tree has {int(sizes.max())} nodes: more than the 65,535 a u16 child index can address')
+        if sizes.size and (sizes == 0).any():
+            raise ValueError('empty tree')
+        local = np.arange(nodes.shape[0], dtype=np.int64) - np.repeat(offsets[:-1].astype(np.int64), sizes)
+        size_of = np.repeat(sizes, sizes)
+        split = nodes['feature'] >= 0
+        for name in ('yes', 'no', 'missing'):
+            child = nodes[name].astype(np.int64)
+            bad = split & ((child <= local) | (child >= size_of))
+            if bad.any():
+                at = int(np.nonzero(bad)[0][0])
+                raise ValueError(f'node {at}: `{name}` child {int(child[at])} is not after its parent inside the tree')
+        if (nodes['feature'] < -1).any():
+            raise ValueError('feature index below -1')
+        return int(nodes['feature'].max()) + 1 if nodes.shape[0] else 0
 
     @property
     def n_trees(self):
@@ -94,6 +120,8 @@ class GbdtModel:
     def predict(self, features):
         """features: float32 [n_rows, n_features] numpy array or CUDA tensor -> predictions float32 [n_rows] of the same kind."""
         n_rows, n_features = int(features.shape[0]), int(features.shape[1])
+        if n_features < self.n_features_needed:
+            raise ValueError(f'the model splits on feature {self.n_features_needed - 1}, the matrix has {n_features} columns')
         if hasattr(features, 'data_ptr'):
             import torch
             nat.expect(features, 'float32', 'features')

@@ -410,6 +410,36 @@ def test_randomised_shapes_against_oracle():
         _check_against_oracle(_tiny_case(truth, queries, n_vocab), k)
 
 
+def test_randomised_posting_shapes_against_oracle():
+    """Fuzz of the posting-list path (k_post needs more than 8,192 rows): vocabularies from 12 columns (every column dense:
+    the accumulators stay zero and the dense patterns decide alone) to 40,000 uniformly drawn ones (no dense column at
+    all), skewed vocabularies in between, queries of up to 250 columns (more than one 32-column group per block), duplicated
+    rows (ties, overflowing candidate buffers), top_n from 1 to 250."""
+    rng = np.random.default_rng(29)
+    for trial in range(14):
+        n_truth = int(rng.choice([8200, 9000, 12345, 20000]))
+        n_vocab = int(rng.choice([12, 60, 500, 5000, 40000]))
+        n_q = int(rng.integers(8, 160))
+        k = int(rng.choice([1, 5, 10, 37, 100, 250]))
+        skewed = trial % 2 == 1
+        weights = 1.0 / np.arange(1, n_vocab + 1) ** (1.1 if skewed else 0.0)
+        weights /= weights.sum()
+
+        def rows_of(count, max_len):
+            lengths = rng.integers(0, min(max_len, n_vocab) + 1, count)
+            drawn = rng.choice(n_vocab, size=int(lengths.sum()), p=weights)
+            return [sorted(set(part.tolist())) for part in np.split(drawn, np.cumsum(lengths)[:-1])]
+        truth = rows_of(n_truth, 30 if trial % 4 else 120)
+        if trial % 3 == 0:                                          # duplicates: hundreds of rows tie at the top
+            for r in rng.integers(0, n_truth, n_truth // 3):
+                truth[int(r)] = truth[int(r) % 7]
+        if not any(truth):
+            truth[0] = [0]
+        queries = rows_of(n_q, 250 if trial % 5 == 0 else 40)
+        queries[0] = truth[5]                                       # an exact copy of a truth row
+        _check_against_oracle(_tiny_case(truth, queries, n_vocab), k)
+
+
 def test_reference_idf_word_vector_on_the_gpu():
     """idf_word('first') = log(3 / 2) = 0.40547 (doppelspeller/tests/test_common.py:25-28) as construct_features emits it."""
     import math

@@ -119,3 +119,20 @@ def test_gbdt_dump_feature_names_and_tree_limit():
     assert abs(model.base_margin - np.log(0.25 / 0.75)) < 1e-6
     linear = gbdt.GbdtModel.from_xgboost_dump(dump, base_score=0.5, objective='reg:squarederror', feature_names=['length', 'ratio'])
     assert linear.transform == gbdt.MARGIN and linear.base_margin == 0.5 and linear.n_trees == 2
+
+
+def test_gbdt_model_rejects_malformed_trees():
+    """The kernel walks device copies of the trees unchecked: GbdtModel validates them once on the host."""
+    import pytest
+    from doppelspeller_b200.gbdt import GbdtModel
+    good = [[(3, 0.5, 1, 2, 1), (-1, 0.1, 0, 0, 0), (-1, -0.2, 0, 0, 0)]]
+    model = GbdtModel.from_trees(good)
+    assert model.n_trees == 1 and model.n_features_needed == 4
+    with pytest.raises(ValueError):
+        GbdtModel.from_trees([[(3, 0.5, 1, 5, 1), (-1, 0.1, 0, 0, 0), (-1, -0.2, 0, 0, 0)]])       # child outside the tree
+    with pytest.raises(ValueError):
+        GbdtModel.from_trees([[(3, 0.5, 0, 2, 1), (-1, 0.1, 0, 0, 0), (-1, -0.2, 0, 0, 0)]])       # child not after its parent
+    with pytest.raises(ValueError):
+        GbdtModel.from_trees([[]])                                                                  # empty tree
+    with pytest.raises(ValueError):
+        model.predict(np.zeros((2, 3), dtype=np.float32))                                           # feature 3 of a 3-column matrix
