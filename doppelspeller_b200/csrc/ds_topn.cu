@@ -79,7 +79,10 @@ constexpr int DENSE_MIN_SHARE = 128;   // a column is dense only if it sits in a
 #define DS_POST_TASKS 8
 #endif
 #ifndef DS_POST_GROWTH
-#define DS_POST_GROWTH 2
+#define DS_POST_GROWTH 3
+#endif
+#ifndef DS_SMALL_BATCH
+#define DS_SMALL_BATCH 32768   // batches up to this many queries sweep with x4 growing ranges
 #endif
 constexpr int POST_RUN = DS_POST_RUN;      // consecutive posting blocks per warp task (the query's columns are loaded once)
 constexpr int POST_DEPTH = DS_POST_DEPTH;  // posting pieces (<= 64 postings each) in flight per warp
@@ -1771,11 +1774,18 @@ static int run_pipeline(Workspace &call_ws, const Index &ix, const QuerySet &qs,
         else if (mode == MODE_ROW) r1 = n;  // the threshold is fixed: one pass over all rows
         else {
             // Growing sweep: thresholds tighten early.  After R rows the threshold is the k-th best of R rows, so about
-            // k * M / R of the next M rows pass it and a range could grow by much more than x2 without overflowing the
-            // candidate buffers - measured (DS_POST_GROWTH = 8: 3 instead of 7 k_post + k_select launches per batch at
-            // 500k rows): 39.6 instead of 38.2 ms per C3 step, because the blocks swept with a stale threshold list more
-            // rows for the full test than the saved launches are worth.  Ranges end on posting-block boundaries.
-            const int64_t growth = r0 >= POST_ROWS ? std::min<int64_t>(DS_POST_GROWTH, std::max<int64_t>(2, 1 + (int64_t)(cand_cap / (2.5 * k)))) : 2;
+            // k * M / R of the next M rows pass it and a range may grow by more than x2 without overflowing the candidate
+            // buffers; but the blocks swept with a stale threshold list more rows for the full test.  Measured per C3 step
+            // (100k queries): x2 37.6 ms, x3 36.6, x4 37.4, x8 39.6.  Small batches (a rank of an 8-GPU run holds 12,500
+            // queries) are bound by the latency of their short launches, not by instructions, and fewer, longer launches
+            // win: 12,500 queries x2 5.95 ms, x3 5.70, x4 5.69, x8 5.83; 25,000 queries x2 11.6, x4 10.9.
+            // Ranges end on posting-block boundaries.  DS_POST_GROWTH in the environment overrides.
+            static const int64_t growth_env = []() {
+                const char *env = getenv("DS_POST_GROWTH");
+                return env ? std::max<int64_t>(2, strtoll(env, nullptr, 10)) : (int64_t)0;
+            }();
+            const int64_t wanted = growth_env > 0 ? growth_env : (n_batch <= DS_SMALL_BATCH ? 4 : DS_POST_GROWTH);
+            const int64_t growth = r0 >= POST_ROWS ? std::min<int64_t>(wanted, std::max<int64_t>(2, 1 + (int64_t)(cand_cap / (2.5 * k)))) : 2;
             r1 = std::max<int64_t>(growth * r0, r0 + dense_rows);
             if (r1 > POST_ROWS) r1 = ceil_div(r1, (int64_t)POST_ROWS) * POST_ROWS;
             r1 = std::min<int64_t>(n, r1);
