@@ -1779,13 +1779,14 @@ static int run_pipeline(Workspace &call_ws, const Index &ix, const QuerySet &qs,
             // (100k queries): x2 37.6 ms, x3 36.6, x4 37.4, x8 39.6.  Small batches (a rank of an 8-GPU run holds 12,500
             // queries) are bound by the latency of their short launches, not by instructions, and fewer, longer launches
             // win: 12,500 queries x2 5.95 ms, x3 5.70, x4 5.69, x8 5.83; 25,000 queries x2 11.6, x4 10.9.
+            // The growth is capped at 1 + cap / (5 k) (top_n = 100: x2 - 73.2 ms per C3 step against 76.5 with x3).
             // Ranges end on posting-block boundaries.  DS_POST_GROWTH in the environment overrides.
             static const int64_t growth_env = []() {
                 const char *env = getenv("DS_POST_GROWTH");
                 return env ? std::max<int64_t>(2, strtoll(env, nullptr, 10)) : (int64_t)0;
             }();
             const int64_t wanted = growth_env > 0 ? growth_env : (n_batch <= DS_SMALL_BATCH ? 4 : DS_POST_GROWTH);
-            const int64_t growth = r0 >= POST_ROWS ? std::min<int64_t>(wanted, std::max<int64_t>(2, 1 + (int64_t)(cand_cap / (2.5 * k)))) : 2;
+            const int64_t growth = r0 >= POST_ROWS ? std::min<int64_t>(wanted, std::max<int64_t>(2, 1 + (int64_t)(cand_cap / (5.0 * k)))) : 2;
             r1 = std::max<int64_t>(growth * r0, r0 + dense_rows);
             if (r1 > POST_ROWS) r1 = ceil_div(r1, (int64_t)POST_ROWS) * POST_ROWS;
             r1 = std::min<int64_t>(n, r1);
