@@ -175,7 +175,7 @@ int ds_gbdt_predict(const float *features, int64_t n_rows, int32_t n_features, c
     const int32_t *d_offsets = nullptr;
     float *d_out = nullptr;
     DS_CHECK(ws.stage_in(&d_features, features, (size_t)n_rows * n_features));
-    DS_CHECK(ws.stage_in(&d_nodes, nodes, (size_t)std::max(1, n_nodes)));
+    if (n_nodes > 0) DS_CHECK(ws.stage_in(&d_nodes, nodes, (size_t)n_nodes));   // an empty model has no node to read (the kernel never looks)
     DS_CHECK(ws.stage_in(&d_offsets, tree_offsets, (size_t)n_trees + 1));
     DS_CHECK(ws.stage_out(&d_out, out, (size_t)n_rows));
     const int32_t zero = 0;

@@ -1,0 +1,131 @@
+"""CPU: the UNMODIFIED kernel sources of doppelspeller_b200/csrc, compiled for the host and executed thread by thread
+(tests/emu/cuda_emu.h: every CUDA thread a fiber, __syncthreads / __syncwarp / shuffles / votes as rendezvous points,
+device allocations as exact-size heap blocks filled with garbage), so that
+
+  * the `gpu` parity tests - golden vectors minted from the reference, the CPU oracle, the fuzzers, the sharded phases,
+    the shared-threshold exchange - also run HERE, where there is no GPU, against the very code the B200 executes;
+  * AddressSanitizer and UBSan check every shared- and global-memory access of the kernels (compute-sanitizer is closed
+    on the GPU pool): out-of-bounds smem / global indexes, misaligned vector loads, reads of freed
+    workspaces, launches that ask for more shared memory than was opted into, collectives whose lanes disagree,
+    barriers that cannot complete, shuffles that read lanes outside the collective, leaked device blocks.
+
+The emulated library is test infrastructure: built into tests/emu/_build/ (git-ignored), loaded only by the
+subprocesses below through DOPPELSPELLER_B200_LIB.  The product has no CPU path (tests/test_library_abi.py).
+"""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, 'tests', 'emu')
+sys.path.insert(0, EMU)
+import build as emu_build  # noqa: E402
+
+SANITIZER_REPORT = re.compile(r'ERROR: AddressSanitizer|runtime error:|ds_emu: FATAL|ds_emu: deadlock|ds_emu: invalid launch')
+SANITIZER_ENV = {'ASAN_OPTIONS': 'detect_leaks=0:detect_stack_use_after_return=0:abort_on_error=0',
+                 'UBSAN_OPTIONS': 'print_stacktrace=1:halt_on_error=1'}
+# DS_EMU_FULL=1: every emulated test under the sanitizers (about five minutes); the default keeps the CPU suite short:
+# the whole set on the plain build, the edge cases / fuzzers / device-pointer paths under the sanitizers
+FULL = os.environ.get('DS_EMU_FULL') == '1'
+EMULATED_FILES = ['tests/test_gpu_parity.py', 'tests/test_gpu_dataframe_api.py', 'tests/emu/device_paths.py']
+SANITIZED_SUBSET = ('edge or randomised_shapes or negative_weight or long_title or large_vocabulary or buffer_overflow or sums_match '
+                    'or indel_ratio_matches_reference or construct_features or levenshtein or idf_word or transform_titles '
+                    'or single_title or prematch or trigram_encoder or title_features or thresholds_shared or pair_kernels '
+                    'or absent_lane or 3000-300-1-3 or 700-100-512-5 or 3-12 or 0-1')
+
+pytestmark = pytest.mark.skipif(sys.platform != 'linux' or os.uname().machine != 'x86_64',
+                                reason='the fiber switch of tests/emu/cuda_emu.cpp is x86-64 System V assembly')
+
+
+def _have_compiler():
+    try:
+        return subprocess.run(['g++', '--version'], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL).returncode == 0
+    except OSError:
+        return False
+
+
+def _run_emulated(library, selection, sanitized, extra=()):
+    env = dict(os.environ, DOPPELSPELLER_B200_LIB=library, DS_EMU_STATS='1')
+    if sanitized:
+        env.update(SANITIZER_ENV, LD_PRELOAD=emu_build.asan_runtime())
+    cmd = [sys.executable, '-m', 'pytest', *EMULATED_FILES, '-m', 'gpu', '-p', 'tests.emu.plugin', '-q', '-x', '-s', '-p', 'no:cacheprovider']   # -s: a sanitizer abort must not die inside pytest's capture
+    if selection:
+        cmd += ['-k', selection]
+    proc = subprocess.run(cmd + list(extra), cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=3000)
+    tail = proc.stdout[-6000:]
+    assert proc.returncode == 0, tail
+    assert not SANITIZER_REPORT.search(proc.stdout), tail
+    summary = re.search(r'(\d+) passed', proc.stdout)
+    assert summary and 'failed' not in proc.stdout.splitlines()[-2], tail
+    stats = re.search(r'ds_emu: (\d+) launches, (\d+) CTAs, (\d+) threads, (\d+) warp collectives, \d+ fiber switches, '
+                      r'(\d+) shuffle reads of absent lanes, (\d+) live device blocks', proc.stdout)
+    assert stats, tail
+    return int(summary.group(1)), [int(x) for x in stats.groups()]
+
+
+@pytest.mark.skipif(not _have_compiler(), reason='g++ not available')
+def test_emulator_reports_planted_faults():
+    """The harness is only evidence if it notices errors: kernels with planted faults (tests/emu/selftest.cu) - an index one
+    past the dynamic / a static shared array, one past a global buffer, a misaligned 128-bit load, a freed buffer, lanes
+    meeting in different collectives, a barrier that cannot complete, > 48 KB of shared memory without the opt-in, an
+    empty grid - must each be reported, and the fault-free kernel must pass."""
+    if emu_build.asan_runtime() is None:
+        pytest.skip('no AddressSanitizer runtime in this toolchain')
+    import translate
+    work = os.path.join(EMU, '_build')
+    os.makedirs(work, exist_ok=True)
+    source = os.path.join(EMU, 'selftest.cu')
+    with open(source) as f:
+        text, launches, dynamic = translate.translate(f.read(), source)
+    assert launches == 10 and dynamic == 2
+    translated = os.path.join(work, 'selftest.emu.cpp')
+    with open(translated, 'w') as f:
+        f.write(text)
+    binary = os.path.join(work, 'selftest')
+    subprocess.run(['g++', '-std=c++17', '-g1', '-O1', '-fno-omit-frame-pointer', '-fsanitize=address,undefined',
+                    '-fno-sanitize-recover=undefined', '-ffp-contract=off', '-frounding-math', '-w', '-I', os.path.join(EMU, 'include'),
+                    '-include', os.path.join(EMU, 'cuda_emu.h'), translated, os.path.join(EMU, 'cuda_emu.cpp'), '-o', binary], check=True)
+    env = dict(os.environ, **SANITIZER_ENV)
+    expected = {
+        'clean': (0, r'selftest clean: ok'),
+        'dynamic-smem-overflow': (None, r'AddressSanitizer: heap-buffer-overflow'),
+        'static-smem-overflow': (None, r"index 64 out of bounds for type 'int \[64\]'"),
+        'global-overflow': (None, r'AddressSanitizer: heap-buffer-overflow'),
+        'misaligned-vector-load': (None, r'misaligned address .* requires 16 byte alignment'),
+        'use-after-free': (None, r'AddressSanitizer: heap-use-after-free'),
+        'mismatched-collectives': (None, r'lanes 0 and 16 meet in different collectives'),
+        'barrier-deadlock': (None, r'ds_emu: deadlock in kernel k_barrier_deadlock'),
+        'smem-without-opt-in': (5, r'invalid launch configuration of k_clean'),
+        'empty-grid': (5, r'invalid launch configuration of k_touch'),
+    }
+    for case, (code, pattern) in expected.items():
+        proc = subprocess.run([binary, case], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+        assert re.search(pattern, proc.stdout), (case, proc.stdout[-2000:])
+        assert (proc.returncode == code) if code is not None else (proc.returncode != 0), (case, proc.returncode)
+
+
+@pytest.mark.skipif(not _have_compiler(), reason='g++ not available')
+def test_kernel_parity_on_the_emulated_device():
+    """Every `gpu` parity test that works on host buffers, plus the device-pointer paths of tests/emu/device_paths.py,
+    against the kernels executed on the host: bit-exact with the golden vectors and the oracle, no shuffle reads a lane
+    outside its collective, every workspace is released."""
+    library = emu_build.build(asan=False)
+    passed, (launches, ctas, threads, collectives, absent, live) = _run_emulated(library, None, sanitized=False)
+    assert passed >= 40
+    assert launches > 2000 and threads > 50_000_000 and collectives > 5_000_000
+    assert absent == 0 and live == 0
+
+
+@pytest.mark.skipif(not _have_compiler(), reason='g++ not available')
+def test_kernels_under_address_and_undefined_behaviour_sanitizers():
+    """The same sources built with -fsanitize=address,undefined: the edge cases, the shape fuzzers and the device-pointer
+    paths (DS_EMU_FULL=1: everything) must pass without a single sanitizer report."""
+    if emu_build.asan_runtime() is None:
+        pytest.skip('no AddressSanitizer runtime in this toolchain')
+    library = emu_build.build(asan=True)
+    passed, (launches, ctas, threads, collectives, absent, live) = _run_emulated(library, None if FULL else SANITIZED_SUBSET, sanitized=True)
+    assert passed >= (40 if FULL else 25)
+    assert absent == 0 and live == 0

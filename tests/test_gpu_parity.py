@@ -277,7 +277,6 @@ def test_construct_features_matches_reference(golden_pairs):
 
 
 def test_construct_features_pairs_table_form(golden_pairs):
-    import torch
     from doppelspeller_b200 import feature_engineering as fe
     g = golden_pairs
     titles = [str(t) for t in g['feat_titles']]
@@ -287,7 +286,12 @@ def test_construct_features_pairs_table_form(golden_pairs):
     got = fe.construct_features_pairs(fe.encode_titles(titles), fe.encode_titles(truths), g['feat_counts'], idx, idx, 1,
                                       int(g['feat_n_truth']))
     assert features_equal(got, g['feat_out'])
-    # device-resident padded layout
+
+
+def test_construct_features_device_resident_padded_layout(golden_pairs):
+    import torch
+    from doppelspeller_b200 import feature_engineering as fe
+    g = golden_pairs
     dev = [torch.as_tensor(g[key]).cuda() for key in ('feat_la', 'feat_lb', 'feat_a', 'feat_b')]
     counts = torch.as_tensor(g['feat_counts'].view(np.int32)).cuda()
     got_dev = fe.construct_features(dev[0], dev[1], dev[2], dev[3], counts, 1, int(g['feat_n_truth']))
@@ -457,17 +461,23 @@ def test_reference_idf_word_vector_on_the_gpu():
 
 # ------------------------------------------------------------------ f3: transform_title
 def test_transform_titles_match_reference(golden_transform):
-    """ds_transform_titles (k_transform) against the reference's transform_title outputs: host and device tables."""
-    import torch
+    """ds_transform_titles (k_transform) against the reference's transform_title outputs: host tables."""
     from doppelspeller_b200 import common
     titles, outputs = golden_transform
     assert common.transform_titles(titles) == outputs
     assert common.transform_title(titles[4500]) == outputs[4500]
+    assert common.transform_titles([]) == []
+
+
+def test_transform_titles_device_table_matches_reference(golden_transform):
+    """the same with the output table left on the device (the form the encoder and the pair kernels consume)"""
+    import torch
+    from doppelspeller_b200 import common
+    titles, outputs = golden_transform
     out, off, raw = common.transform_titles_table(titles, device=torch.cuda.current_device(), warn=False)
     out, off = out.cpu().numpy(), off.cpu().numpy()
     blob = out.tobytes().decode('latin-1')
     assert [blob[off[i]:off[i + 1]] for i in range(len(titles))] == outputs
-    assert common.transform_titles([]) == []
     # raw_len = len(text) before the [:255] cut (drives the reference's two warnings)
     assert int(raw[titles.index('x' * 256)]) == 256 and int(raw[titles.index('--')]) == 0
 
@@ -495,21 +505,33 @@ def _random_forest(rng, n_trees, n_features, max_depth):
 
 
 @pytest.mark.parametrize('n_trees,max_depth', [(300, 5), (1000, 5), (3, 12), (0, 1)])
-def test_gbdt_predict_matches_oracle(n_trees, max_depth):
-    import torch
+def _gbdt_case(n_trees, max_depth):
     from doppelspeller_b200 import gbdt
-    from oracle import oracle
     rng = np.random.default_rng(100 + n_trees)
     model = gbdt.GbdtModel.from_trees(_random_forest(rng, n_trees, 66, max_depth), base_margin=-0.4, transform=gbdt.LOGISTIC)
     x = rng.normal(0, 50, size=(20011, 66)).astype(np.float32)
     x[rng.random(x.shape) < 0.08] = np.nan
     x[rng.random(x.shape) < 0.01] = np.inf
     x[:, 5] = np.round(x[:, 5])                      # values that land exactly on thresholds exercise the strict `<`
+    return model, x
+
+
+@pytest.mark.parametrize('n_trees,max_depth', [(300, 5), (3, 12)])
+def test_gbdt_predict_device_resident_features(n_trees, max_depth):
+    import torch
+    model, x = _gbdt_case(n_trees, max_depth)
+    got_dev = model.predict(torch.as_tensor(x).cuda()).cpu().numpy()
+    assert np.array_equal(got_dev.view(np.uint32), model.predict(x).view(np.uint32))
+
+
+@pytest.mark.parametrize('n_trees,max_depth', [(300, 5), (1000, 5), (3, 12), (0, 1)])
+def test_gbdt_predict_matches_oracle(n_trees, max_depth):
+    from doppelspeller_b200 import gbdt
+    from oracle import oracle
+    model, x = _gbdt_case(n_trees, max_depth)
     want = oracle.gbdt_predict(x, model.nodes, model.tree_offsets, model.base_margin, logistic=True)
     got = model.predict(x)
     assert np.allclose(got, want, rtol=1e-6, atol=0)
-    got_dev = model.predict(torch.as_tensor(x).cuda()).cpu().numpy()
-    assert np.array_equal(got_dev.view(np.uint32), got.view(np.uint32))
     margin_model = gbdt.GbdtModel(model.nodes, model.tree_offsets, model.base_margin, gbdt.MARGIN)
     want_margin = oracle.gbdt_predict(x, model.nodes, model.tree_offsets, model.base_margin, logistic=False)
     assert np.array_equal(margin_model.predict(x).view(np.uint32), want_margin.view(np.uint32))   # float32 sums: bit exact
