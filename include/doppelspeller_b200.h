@@ -215,6 +215,12 @@ int ds_topn_rescan(ds_index *index, int64_t n_q, const int64_t *q_row_ptr, const
 int ds_indel_ratio_u8(const uint8_t *a, const uint8_t *b, int64_t stride, const uint8_t *la, const uint8_t *lb,
                       int64_t n, uint8_t *out_ratio, uint16_t *out_dist, void *stream);
 
+/* Device-resident string buffers (the [n, stride] code rows above, the byte tables below) are fetched in ALIGNED 32-bit
+ * words: the word that holds a buffer's last byte is read whole, so a device allocation must be readable up to the next
+ * 4-byte boundary past its last byte.  Every cudaMalloc / cudaMallocAsync / torch allocation is (256-byte granules);
+ * host buffers are staged into workspaces the library rounds up itself.  Checked under AddressSanitizer by the host
+ * emulation of the kernels (tests/emu), which is where this contract was found to be implicit. */
+
 /* Same arithmetic on a compact title table: pair p compares table_a[idx_a[p]] with table_b[idx_b[p]];
  * a table is (bytes, offsets[n_titles+1]); titles longer than 255 bytes are truncated like
  * FeatureEngineering.encode_title does.  This is the B200 layout (no [P,255] materialisation). */

@@ -12,6 +12,26 @@
 #define DS_EMU_ASAN 0
 #endif
 
+// ThreadSanitizer build (build.py --tsan): the kernel sources are instrumented, this file is not.  Every CUDA thread is a
+// TSan fiber (the 1,024 fibers are created once and reused CTA after CTA); fiber switches carry NO synchronisation, the
+// happens-before edges are exactly CUDA's: launch -> every thread of a CTA -> end of the CTA (CTAs are ordered one after
+// the other: the scope is that of compute-sanitizer's racecheck, hazards INSIDE a CTA), __syncthreads between the threads
+// of the CTA, __syncwarp between the lanes it names.  Votes / shuffles / reductions order memory only when
+// DS_EMU_COLLECTIVES_ORDER=1 (the programming guide promises it for __syncwarp alone).
+#if defined(__SANITIZE_THREAD__) || defined(DS_EMU_TSAN)
+#define DS_EMU_RACECHECK 1
+extern "C" {
+void *__tsan_get_current_fiber(void);
+void *__tsan_create_fiber(unsigned flags);
+void __tsan_destroy_fiber(void *fiber);
+void __tsan_switch_to_fiber(void *fiber, unsigned flags);
+void __tsan_acquire(void *addr);
+void __tsan_release(void *addr);
+}
+#else
+#define DS_EMU_RACECHECK 0
+#endif
+
 #undef threadIdx
 #undef blockIdx
 #undef blockDim
@@ -43,6 +63,7 @@ struct Fiber : ThreadCtx {
     unsigned mask = 0;
     uint64_t value = 0, result = 0;
     void *asan_fake_stack = nullptr;
+    void *tsan_fiber = nullptr;
 };
 
 struct Engine {
@@ -55,6 +76,11 @@ struct Engine {
     const char *kernel = "";
     std::map<const void *, size_t> granted_smem;
     cudaError_t last_error = cudaSuccess;
+    void *scheduler_tsan_fiber = nullptr;
+    bool collectives_order_memory = false;
+    // addresses ThreadSanitizer keeps vector clocks for (contents unused)
+    char sync_cta_start = 0, sync_cta_done = 0, sync_barrier = 0;
+    std::map<uint64_t, char> sync_warp;   // (warp, mask) -> clock of that group of lanes
     // statistics, printed when DS_EMU_STATS is set
     uint64_t launches = 0, ctas = 0, threads = 0, collectives = 0, switches = 0, reads_of_absent_lanes = 0;
 };
@@ -106,6 +132,9 @@ inline void to_scheduler(Fiber *self, bool dying) {
     __sanitizer_start_switch_fiber(dying ? nullptr : &self->asan_fake_stack, g_main_stack_bottom, g_main_stack_size);
 #endif
     (void)dying;
+#if DS_EMU_RACECHECK
+    __tsan_switch_to_fiber(g.scheduler_tsan_fiber, 1 /* no synchronisation */);
+#endif
     ds_emu_switch(&self->sp, g.scheduler_sp);
 #if DS_EMU_ASAN
     __sanitizer_finish_switch_fiber(self->asan_fake_stack, nullptr, nullptr);
@@ -117,12 +146,21 @@ void trampoline() {
     __sanitizer_finish_switch_fiber(nullptr, &g_main_stack_bottom, &g_main_stack_size);
 #endif
     Fiber *self = static_cast<Fiber *>(g_cur);
+#if DS_EMU_RACECHECK
+    __tsan_acquire(&g.sync_cta_start);
+#endif
     (*g.body)();
+#if DS_EMU_RACECHECK
+    __tsan_release(&g.sync_cta_done);
+#endif
     self->state = DONE;
 #if DS_EMU_ASAN
     __sanitizer_start_switch_fiber(nullptr, g_main_stack_bottom, g_main_stack_size);
 #endif
     ++g.switches;
+#if DS_EMU_RACECHECK
+    __tsan_switch_to_fiber(g.scheduler_tsan_fiber, 1);
+#endif
     ds_emu_switch(&self->sp, g.scheduler_sp);
     die("a finished CUDA thread was resumed");
 }
@@ -131,6 +169,10 @@ void resume(Fiber *f) {
     g_cur = f;
 #if DS_EMU_ASAN
     __sanitizer_start_switch_fiber(&g.scheduler_fake_stack, f->stack, STACK_BYTES);
+#endif
+#if DS_EMU_RACECHECK
+    if (f->tsan_fiber == nullptr) f->tsan_fiber = __tsan_create_fiber(0);
+    __tsan_switch_to_fiber(f->tsan_fiber, 1 /* no synchronisation */);
 #endif
     ds_emu_switch(&g.scheduler_sp, f->sp);
 #if DS_EMU_ASAN
@@ -249,6 +291,9 @@ void release_barrier_if_complete() {
 }
 
 void run_cta() {
+#if DS_EMU_RACECHECK
+    __tsan_release(&g.sync_cta_start);
+#endif
     g.n_live = g.n_threads;
     g.n_at_barrier = 0;
     int pending = g.n_threads;
@@ -281,6 +326,9 @@ void run_cta() {
             abort();
         }
     }
+#if DS_EMU_RACECHECK
+    __tsan_acquire(&g.sync_cta_done);
+#endif
 }
 
 struct Allocation {
@@ -302,10 +350,14 @@ const Allocation *find_allocation(const void *p, uintptr_t *base_out = nullptr) 
 
 struct Stats {
     ~Stats() {
-        if (getenv("DS_EMU_STATS"))
-            fprintf(stderr, "ds_emu: %llu launches, %llu CTAs, %llu threads, %llu warp collectives, %llu fiber switches, %llu shuffle reads of absent lanes, %zu live device blocks\n",
+        const char *where = getenv("DS_EMU_STATS");   // "1": stderr; a path: appended there (one line per process)
+        FILE *out = where == nullptr ? nullptr : (where[0] == '/' ? fopen(where, "a") : stderr);
+        if (out != nullptr) {
+            fprintf(out, "ds_emu: %llu launches, %llu CTAs, %llu threads, %llu warp collectives, %llu fiber switches, %llu shuffle reads of absent lanes, %zu live device blocks\n",
                     (unsigned long long)g.launches, (unsigned long long)g.ctas, (unsigned long long)g.threads, (unsigned long long)g.collectives,
                     (unsigned long long)g.switches, (unsigned long long)g.reads_of_absent_lanes, g_device_memory.size());
+            if (out != stderr) fclose(out);
+        }
     }
 } g_stats;
 
@@ -321,9 +373,19 @@ uint64_t warp_collective(int op, unsigned mask, uint64_t value, int arg, int wid
     self->arg = arg;
     self->width = width;
     self->state = WAIT_WARP;
+#if DS_EMU_RACECHECK
+    char *clock = nullptr;
+    if (op == OP_SYNCWARP || g.collectives_order_memory) {
+        clock = &g.sync_warp[((uint64_t)self->warp << 32) | mask];
+        __tsan_release(clock);
+    }
+#endif
     try_complete(self->warp, mask);
     if (self->state != READY) to_scheduler(self, false);
     if (self->state != READY) die("a waiting CUDA thread was resumed");
+#if DS_EMU_RACECHECK
+    if (clock != nullptr) __tsan_acquire(clock);
+#endif
     return self->result;
 }
 
@@ -332,8 +394,14 @@ void cta_barrier() {
     if (self == nullptr) die("__syncthreads outside a kernel");
     self->state = WAIT_CTA;
     ++g.n_at_barrier;
+#if DS_EMU_RACECHECK
+    __tsan_release(&g.sync_barrier);
+#endif
     release_barrier_if_complete();
     if (self->state != READY) to_scheduler(self, false);
+#if DS_EMU_RACECHECK
+    __tsan_acquire(&g.sync_barrier);
+#endif
 }
 
 void launch(const void *fn, const char *name, dim3 grid, dim3 block, size_t smem, cudaStream_t, const std::function<void()> &body) {
@@ -351,6 +419,11 @@ void launch(const void *fn, const char *name, dim3 grid, dim3 block, size_t smem
         return;
     }
     ++g.launches;
+#if DS_EMU_RACECHECK
+    g.scheduler_tsan_fiber = __tsan_get_current_fiber();
+    g.collectives_order_memory = getenv("DS_EMU_COLLECTIVES_ORDER") != nullptr;
+    g.sync_warp.clear();
+#endif
     g.kernel = name;
     g.body = &body;
     g.n_threads = (int)n_threads;
@@ -486,9 +559,12 @@ cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) {
 }
 
 // device buffers for tests that hand the library DEVICE pointers (used in place instead of being staged)
+// (sizes are rounded up to 16 bytes: the caller's allocator - cudaMalloc, torch - hands out 256-byte granules at least, and
+// the string kernels rely on that when they fetch the aligned 32-bit word that holds a table's last byte; the library's OWN
+// workspaces keep their exact size, Workspace::alloc rounds them itself)
 extern "C" void *ds_emu_malloc(size_t bytes) {
     void *p = nullptr;
-    return cudaMallocAsync(&p, bytes, nullptr) == cudaSuccess ? p : nullptr;
+    return cudaMallocAsync(&p, (bytes + 15) & ~(size_t)15, nullptr) == cudaSuccess ? p : nullptr;
 }
 extern "C" void ds_emu_free(void *p) { cudaFreeAsync(p, nullptr); }
 

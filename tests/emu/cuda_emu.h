@@ -211,22 +211,35 @@ inline unsigned __reduce_and_sync(unsigned mask, unsigned v) { return (unsigned)
 inline unsigned __reduce_xor_sync(unsigned mask, unsigned v) { return (unsigned)::ds_emu::warp_collective(::ds_emu::OP_RED_XOR, mask, v, 0, 32); }
 
 // ------------------------------------------------------------------------------------------------ atomics (one fiber runs at a time)
+// (relaxed __atomic builtins: the same code for one fiber at a time, and ThreadSanitizer knows the access is atomic)
 template <typename T, typename U>
-inline T atomicAdd(T *p, U v) { T old = *p; *p = (T)(old + (T)v); return old; }
+inline T atomicAdd(T *p, U v) { return __atomic_fetch_add(p, (T)v, __ATOMIC_RELAXED); }
 template <typename T, typename U>
-inline T atomicSub(T *p, U v) { T old = *p; *p = (T)(old - (T)v); return old; }
+inline T atomicSub(T *p, U v) { return __atomic_fetch_sub(p, (T)v, __ATOMIC_RELAXED); }
 template <typename T, typename U>
-inline T atomicOr(T *p, U v) { T old = *p; *p = (T)(old | (T)v); return old; }
+inline T atomicOr(T *p, U v) { return __atomic_fetch_or(p, (T)v, __ATOMIC_RELAXED); }
 template <typename T, typename U>
-inline T atomicAnd(T *p, U v) { T old = *p; *p = (T)(old & (T)v); return old; }
+inline T atomicAnd(T *p, U v) { return __atomic_fetch_and(p, (T)v, __ATOMIC_RELAXED); }
 template <typename T, typename U>
-inline T atomicMax(T *p, U v) { T old = *p; if ((T)v > old) *p = (T)v; return old; }
-template <typename T, typename U>
-inline T atomicMin(T *p, U v) { T old = *p; if ((T)v < old) *p = (T)v; return old; }
-template <typename T, typename U>
-inline T atomicExch(T *p, U v) { T old = *p; *p = (T)v; return old; }
+inline T atomicExch(T *p, U v) { return __atomic_exchange_n(p, (T)v, __ATOMIC_RELAXED); }
 template <typename T, typename U, typename V>
-inline T atomicCAS(T *p, U compare, V v) { T old = *p; if (old == (T)compare) *p = (T)v; return old; }
+inline T atomicCAS(T *p, U compare, V v) {
+    T expected = (T)compare;
+    __atomic_compare_exchange_n(p, &expected, (T)v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED);
+    return expected;
+}
+template <typename T, typename U>
+inline T atomicMax(T *p, U v) {
+    T old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while ((T)v > old && !__atomic_compare_exchange_n(p, &old, (T)v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
+template <typename T, typename U>
+inline T atomicMin(T *p, U v) {
+    T old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while ((T)v < old && !__atomic_compare_exchange_n(p, &old, (T)v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
 
 // ------------------------------------------------------------------------------------------------ loads, bit tricks
 template <typename T>

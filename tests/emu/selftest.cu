@@ -64,6 +64,26 @@ __global__ void k_misaligned_vector_load(const unsigned char *bytes, uint4 *out)
     out[threadIdx.x] = *reinterpret_cast<const uint4 *>(bytes + 4 + 16 * threadIdx.x);
 }
 
+// racecheck cases (ThreadSanitizer build): a neighbour's shared-memory value is read without the barrier that orders it
+__global__ void k_race_missing_syncthreads(int *out) {
+    __shared__ int s_tile[128];
+    s_tile[threadIdx.x] = (int)threadIdx.x;
+    out[threadIdx.x] = s_tile[(threadIdx.x + 32) & 127];      // another warp's element: needs __syncthreads()
+}
+
+__global__ void k_race_missing_syncwarp(int *out) {
+    __shared__ int s_tile[32];
+    s_tile[threadIdx.x] = (int)threadIdx.x;
+    out[threadIdx.x] = s_tile[threadIdx.x ^ 1];               // the neighbouring lane's element: needs __syncwarp()
+}
+
+__global__ void k_ordered_by_syncwarp(int *out) {
+    __shared__ int s_tile[32];
+    s_tile[threadIdx.x] = (int)threadIdx.x;
+    __syncwarp();
+    out[threadIdx.x] = s_tile[threadIdx.x ^ 1];
+}
+
 __global__ void k_touch(const int *in, int *out) { out[threadIdx.x] = in[threadIdx.x]; }
 
 #define CHECK(expr)                                                                         \
@@ -115,6 +135,12 @@ int main(int argc, char **argv) {
         k_barrier_deadlock<<<1, 32, 0, nullptr>>>(d_out);
     } else if (!strcmp(which, "misaligned-vector-load")) {
         k_misaligned_vector_load<<<1, 8, 0, nullptr>>>(reinterpret_cast<const unsigned char *>(d_in), reinterpret_cast<uint4 *>(d_out));
+    } else if (!strcmp(which, "race-missing-syncthreads")) {
+        k_race_missing_syncthreads<<<1, 128, 0, nullptr>>>(d_out);
+    } else if (!strcmp(which, "race-missing-syncwarp")) {
+        k_race_missing_syncwarp<<<1, 32, 0, nullptr>>>(d_out);
+    } else if (!strcmp(which, "ordered-by-syncwarp")) {
+        k_ordered_by_syncwarp<<<2, 32, 0, nullptr>>>(d_out);
     } else if (!strcmp(which, "use-after-free")) {
         CHECK(cudaFreeAsync(d_in, nullptr));
         k_touch<<<1, 32, 0, nullptr>>>(d_in, d_out);
