@@ -42,7 +42,7 @@ def ascii_of_codepoint_table():
 
 def _utf32_table(titles):
     """(code points uint32[total], offsets int64[n+1]) of python strings."""
-    lengths = np.fromiter((len(t) for t in titles), dtype=np.int64, count=len(titles))
+    lengths = np.fromiter(map(len, titles), dtype=np.int64, count=len(titles))
     offsets = np.zeros(len(titles) + 1, dtype=np.int64)
     np.cumsum(lengths, out=offsets[1:])
     data = np.frombuffer(''.join(titles).encode('utf-32-le', 'surrogatepass'), dtype=np.uint32)
@@ -106,13 +106,12 @@ def transform_title(title):
 
 def _string_table(texts):
     """(bytes uint8[total], offsets int64[n+1]) of latin-1 encodable strings."""
-    encoded = [t.encode('latin-1') for t in texts]
-    lengths = np.fromiter((len(e) for e in encoded), dtype=np.int64, count=len(encoded))
+    lengths = np.fromiter(map(len, texts), dtype=np.int64, count=len(texts))      # latin-1: one byte per character
     if lengths.size and lengths.max() > nat.MAX_TITLE:
         raise ValueError('titles longer than 255 characters are outside the domain of the ratio kernels')
-    offsets = np.zeros(len(encoded) + 1, dtype=np.int64)
+    offsets = np.zeros(len(texts) + 1, dtype=np.int64)
     np.cumsum(lengths, out=offsets[1:])
-    data = np.frombuffer(b''.join(encoded), dtype=np.uint8)
+    data = np.frombuffer(''.join(texts).encode('latin-1'), dtype=np.uint8)
     if data.size == 0:
         data = np.zeros(1, dtype=np.uint8)
     return np.array(data), offsets      # a writable copy (np.frombuffer views are read-only)

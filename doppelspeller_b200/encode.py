@@ -81,11 +81,13 @@ def trigram_text(code):
 
 def title_table(titles):
     """Compact (bytes uint8[total], offsets int64[n+1]) table of ASCII titles (truncated to 255 like transform_title)."""
-    clipped = [t[:255] for t in titles]
-    lengths = np.fromiter((len(t) for t in clipped), dtype=np.int64, count=len(clipped))
-    offsets = np.zeros(len(clipped) + 1, dtype=np.int64)
+    lengths = np.fromiter(map(len, titles), dtype=np.int64, count=len(titles))       # C-level iteration: no generator frame per title
+    if lengths.size and lengths.max() > 255:
+        titles = [t[:255] for t in titles]
+        np.minimum(lengths, 255, out=lengths)
+    offsets = np.zeros(len(titles) + 1, dtype=np.int64)
     np.cumsum(lengths, out=offsets[1:])
-    data = np.frombuffer(''.join(clipped).encode('latin-1', 'replace'), dtype=np.uint8)
+    data = np.frombuffer(''.join(titles).encode('latin-1', 'replace'), dtype=np.uint8)
     return (np.array(data) if data.size else np.zeros(1, dtype=np.uint8)), offsets
 
 

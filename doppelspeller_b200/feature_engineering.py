@@ -125,7 +125,11 @@ def encode_title(title):
 
 def encode_titles(titles):
     """Compact table form used by the *_pairs kernels: (codes uint8[total], offsets int64[n+1])."""
-    joined = ''.join(t[:MAX_CHARACTERS_ALLOWED_IN_THE_TITLE] for t in titles)
+    lengths = np.fromiter(map(len, titles), dtype=np.int64, count=len(titles))
+    if lengths.size and lengths.max() > MAX_CHARACTERS_ALLOWED_IN_THE_TITLE:
+        titles = [t[:MAX_CHARACTERS_ALLOWED_IN_THE_TITLE] for t in titles]
+        np.minimum(lengths, MAX_CHARACTERS_ALLOWED_IN_THE_TITLE, out=lengths)
+    joined = ''.join(titles)
     lut = np.full(256, 255, dtype=np.uint8)
     for ch, code in ENCODING.items():
         lut[ord(ch)] = code
@@ -134,8 +138,6 @@ def encode_titles(titles):
     if codes.size and codes.max() == 255:
         bad = chr(int(raw[np.argmax(codes == 255)]))
         raise KeyError(bad)                              # encode_title would fail on self.encoding.get -> None
-    lengths = np.fromiter((min(len(t), MAX_CHARACTERS_ALLOWED_IN_THE_TITLE) for t in titles), dtype=np.int64,
-                          count=len(titles))
     offsets = np.zeros(len(titles) + 1, dtype=np.int64)
     np.cumsum(lengths, out=offsets[1:])
     return codes, offsets
