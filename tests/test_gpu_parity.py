@@ -314,6 +314,10 @@ def test_levenshtein_ratio_and_prematch_against_oracle(example_titles):
     assert np.array_equal(got, want)
     assert common.levenshtein_ratio('coolblu bv', 'coolblue bv') == 95
     assert common.levenshtein_token_sort_ratio('bv coolblue', 'coolblue bv') == 100
+    from tests.test_oracle_golden import PUBLISHED_LEVENSHTEIN_ANSWERS          # python-Levenshtein docstring, fuzzywuzzy README
+    for x, y, ratio, token_sort in PUBLISHED_LEVENSHTEIN_ANSWERS:
+        assert common.levenshtein_ratio(x, y) == ratio and common.levenshtein_ratio(y, x) == ratio
+        assert token_sort is None or common.levenshtein_token_sort_ratio(x, y) == token_sort
     xs2, ys2 = xs[:-5], ys[:-5]
     got = predict.get_levenshtein_ratios(xs2, ys2)
     want = np.array([oracle.prematch_ratio(x, y) for x, y in zip(xs2, ys2)])

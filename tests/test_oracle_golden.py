@@ -89,6 +89,24 @@ def test_levenshtein_ratio_known_answers():
     assert oracle.prematch_ratio('a' * 10, 'a' * 30) == 0                        # length pre-filter (predict.py:150)
 
 
+# The only answers the absent third-party code itself publishes: python-Levenshtein's docstring of ratio()
+# (0.583333... and 0.0) and fuzzywuzzy's README, whose fuzz.ratio / token_sort_ratio are int(round(100 * Levenshtein ratio))
+# when python-Levenshtein is installed - the same expression as common.py:161-167.  Anchors, not a pin: see DESIGN.md section 2.
+PUBLISHED_LEVENSHTEIN_ANSWERS = (
+    ('Hello world!', 'Holly grail!', 58, None), ('Brian', 'Jesus', 0, None),
+    ('this is a test', 'this is a test!', 97, None),
+    ('fuzzy wuzzy was a bear', 'wuzzy fuzzy was a bear', 91, 100),
+)
+
+
+def test_levenshtein_ratio_published_answers_of_the_third_party_libraries():
+    for x, y, ratio, token_sort in PUBLISHED_LEVENSHTEIN_ANSWERS:
+        assert oracle.levenshtein_ratio(x, y) == ratio
+        assert oracle.levenshtein_ratio(y, x) == ratio
+        if token_sort is not None:
+            assert oracle.levenshtein_token_sort_ratio(x, y) == token_sort
+
+
 def test_transform_title_matches_reference(golden_transform):
     """common.py:20-47 on 7,016 raw titles (example data + seeded accents / white space / length edge cases) and the
     reference's own test vector (doppelspeller/tests/test_common.py:16-19)."""
