@@ -93,6 +93,34 @@ def test_fast_levenshtein_ratio_random(ref):
         assert oracle.indel_ratio_u8(a, b) == int(flr(a, b))
 
 
+def test_levenshtein_ratio_distance_recovered_from_the_reference_kernel(ref):
+    """a5 cross-check of SURVEY 8(c): python-levenshtein is absent, but the reference's own jitted fast_levenshtein_ratio
+    computes the same distance d (feature_engineering.py:50-61).  For la + lb <= 100 consecutive admissible d (same parity
+    as la + lb) move the truncated ratio by >= 2, so d is recovered uniquely from the reference's output; common.py:162's
+    expression int(round(ratio * 100)) with ratio = (la + lb - d) / (la + lb), evaluated by Python itself, must then be
+    what oracle.levenshtein_ratio returns (distance AND half-even rounding)."""
+    rng = np.random.default_rng(5)
+    flr = ref.feature_engineering.fast_levenshtein_ratio
+    alphabet = np.frombuffer(b'abcdefgh ', dtype=np.uint8)
+    halves = 0
+    for trial in range(4000):
+        la = int(rng.integers(1, 50))
+        lb = int(rng.integers(1, 101 - la)) if trial % 4 else la            # equal lengths: the x.5 ties (e.g. 14/16)
+        a = alphabet[rng.integers(0, int(rng.integers(2, 10)), la)]
+        b = a.copy()[:lb] if trial % 3 == 0 and lb <= la else alphabet[rng.integers(0, 9, lb)]
+        if trial % 3 == 0:
+            b = b.copy()
+            b[rng.integers(0, len(b), 1 + len(b) // 8)] = alphabet[int(rng.integers(0, 9))]
+        total = la + len(b)
+        got = int(flr(np.ascontiguousarray(a), np.ascontiguousarray(b)))
+        candidates = [d for d in range(total % 2, total + 1, 2) if -1e-9 <= 100.0 * (total - d) / total - got < 1.0 + 1e-9]
+        assert len(candidates) == 1, (total, got, candidates)
+        want = int(round((total - candidates[0]) / total * 100))
+        halves += (200 * (total - candidates[0])) % (2 * total) == total
+        assert oracle.levenshtein_ratio(a.tobytes().decode(), b.tobytes().decode()) == want
+    assert halves > 20                                                       # the half-even branch was exercised
+
+
 def test_construct_features_random(ref, example):
     rng = np.random.default_rng(2)
     c = ref.constants
