@@ -55,6 +55,9 @@ def run(device=None, reference_rows=1000, reference_pairs=60000, feature_queries
     out = {'config': f'example data: {n_q} test x {n_truth} truth titles, top_n = {TOP_N}', 'host_cores': cores}
 
     # ---- C1: index build + candidates ----
+    # untimed warm-up of the same calls: CUDA module load and the growth of the stream-ordered workspace pool are one-time
+    # costs of the process (0.26 s in one record, 0 in the next), excluded like the reference's numba JIT below
+    MatchMaker(test.copy(), truth.copy(), TOP_N).get_closest_matches(0)
     build_s, mm = _timed(lambda: MatchMaker(test.copy(), truth.copy(), TOP_N))
     loop_first_s, _ = _timed(lambda: mm.get_closest_matches(0))                  # the first call computes every row on the GPU
     loop_s, ours_ids = _timed(lambda: [mm.get_closest_matches(q) for q in range(n_q)])
