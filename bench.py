@@ -725,7 +725,7 @@ def second_workload(args, device):
 def c4_pairs(device):
     """BASELINE configs[3]: 100M synthetic candidate pairs, titles up to 128 characters (bench_pairs.py)."""
     import bench_pairs
-    out = bench_pairs.run(pairs=100_000_000, titles=400_000, steps=2, sample=100_000, chunk=25_000_000, device=device)
+    out = bench_pairs.run(pairs=100_000_000, titles=400_000, steps=2, sample=1_000_000, chunk=25_000_000, device=device)
     # the byte convention of SURVEY.md 8(d) next to what ncu measured: both kernels are bound by instruction issue / latency
     # (bit-parallel alignments in registers and shared memory), not by the bytes of the strings
     out['indel_ratio']['measured_limiter'] = measured_limiter('k_indel_pairs')
