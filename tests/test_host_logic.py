@@ -136,3 +136,31 @@ def test_gbdt_model_rejects_malformed_trees():
         GbdtModel.from_trees([[]])                                                                  # empty tree
     with pytest.raises(ValueError):
         model.predict(np.zeros((2, 3), dtype=np.float32))                                           # feature 3 of a 3-column matrix
+
+
+def test_combine_rescans_matches_the_plain_loop():
+    """sharded.combine_rescans (vectorised, device side in production) against its definition: every shard reports its k
+    highest qualifying rows in descending order; shards are ascending row ranges, so the answer is the concatenation from
+    the highest shard down, cut at k, padded with -1."""
+    import torch
+
+    from doppelspeller_b200 import sharded
+    rng = np.random.default_rng(17)
+    for n_shards, n_f, k in ((1, 5, 3), (2, 40, 10), (3, 33, 1), (5, 64, 7), (8, 17, 100), (4, 0, 5)):
+        counts = rng.integers(0, k + 1, size=(n_shards, n_f)).astype(np.int32)
+        counts[:, : n_f // 4] = 0                                    # queries no shard has a row for
+        counts[-1, n_f // 4: n_f // 2] = k                           # the highest shard alone fills the answer
+        rows = np.full((n_shards, n_f, k), -1, dtype=np.int64)
+        for s in range(n_shards):
+            for f in range(n_f):
+                picked = np.sort(rng.choice(1000, size=counts[s, f], replace=False))[::-1] + 1000 * s
+                rows[s, f, :counts[s, f]] = picked
+        want = np.full((n_f, k), -1, dtype=np.int64)
+        want_count = np.zeros(n_f, dtype=np.int32)
+        for f in range(n_f):
+            merged = [int(r) for s in range(n_shards - 1, -1, -1) for r in rows[s, f, :counts[s, f]]][:k]
+            want[f, :len(merged)] = merged
+            want_count[f] = len(merged)
+        got, got_count = sharded.combine_rescans(torch.as_tensor(rows), torch.as_tensor(counts), k)
+        assert np.array_equal(got.numpy(), want) and np.array_equal(got_count.numpy(), want_count)
+        assert got_count.dtype == torch.int32 and got.dtype == torch.int64
