@@ -66,6 +66,33 @@ def test_candidate_lists(ref, example, k):
         assert mm.get_closest_matches(q) == title_ids[rows[q]].tolist()
 
 
+@pytest.mark.parametrize('n_truth,n_q,k,seed', [(3000, 120, 10, 41), (900, 60, 100, 42), (64, 40, 64, 43)])
+def test_candidate_lists_on_the_synthetic_workload(ref, n_truth, n_q, k, seed):
+    """The reference's own MatchMaker on titles of the BENCH generator (doppelspeller_b200.synthetic: heavier duplication,
+    pseudo-words, edited copies of truth titles as queries - shapes the example data does not have), row by row against
+    the oracle; the last case has top_n == number of truth rows (every row returned, match_maker.py:66-71)."""
+    import pandas as pd
+
+    from doppelspeller_b200 import synthetic
+    c = ref.constants
+    truth_titles = synthetic.generate_truth_titles(n_truth, seed=seed)
+    test_titles, _ = synthetic.generate_test_titles(truth_titles, n_q, seed=seed + 100)
+
+    def frame(titles, first_id):
+        return pd.DataFrame({c.COLUMN_TITLE_ID: np.arange(first_id, first_id + len(titles)),
+                             c.COLUMN_TRANSFORMED_TITLE: list(titles),
+                             c.COLUMN_N_GRAMS: [ref.common.get_n_grams(t, 3) for t in titles]})
+    truth, test = frame(truth_titles, 5000), frame(test_titles, 0)
+    mm = ref.match_maker.MatchMaker(test.copy(), truth.copy(), k)
+    index = oracle.finish_index(oracle.encode_reference_order(list(test[c.COLUMN_N_GRAMS]), list(truth[c.COLUMN_N_GRAMS])))
+    assert np.array_equal(mm.sums_matrix_truth.view(np.uint32), index['sums'].view(np.uint32))
+    rows, count, _ = oracle.topn(index, k)
+    assert (count == k).all()
+    title_ids = truth[c.COLUMN_TITLE_ID].to_numpy()
+    for q in range(n_q):
+        assert mm.get_closest_matches(q) == title_ids[rows[q]].tolist()
+
+
 def test_fast_arg_top_k_random(ref):
     rng = np.random.default_rng(0)
     fatk = ref.match_maker.fast_arg_top_k
