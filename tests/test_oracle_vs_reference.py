@@ -156,6 +156,11 @@ def test_construct_features_random(ref, example):
     pairs = [(test_titles[i % N_QUERIES], truth_titles[int(rng.integers(0, len(truth_titles)))]) for i in range(600)]
     words = ['ab', 'cde', 'fghi', 'jk', 'lmnop', 'q', 'rst', 'uv', 'wxyz', 'a1', 'b22', 'c333', 'dd', 'ee', 'ffg', 'hh']
     pairs += [(' '.join(rng.choice(words, max(1, n - 1))), ' '.join(rng.choice(words, n))) for n in range(1, 21) for _ in range(5)]
+    # C4's stress slice and beyond: 65..255 characters, incl. la + lb > 255 (the uint8 cells of the DP wrap) and > 15 words
+    for n_a, n_b in [(int(rng.integers(14, 70)), int(rng.integers(14, 70))) for _ in range(160)]:
+        a, b = ' '.join(rng.choice(words, n_a))[:255].strip(), ' '.join(rng.choice(words, n_b))[:255].strip()
+        pairs.append((a, b if rng.random() < 0.5 else (a[:int(rng.integers(1, len(a)))].strip() + ' ' + b[:100].strip())[:255].strip()))
+    assert sum(len(a) + len(b) > 255 for a, b in pairs) > 20 and max(len(b) for a, b in pairs) <= 255
     la = np.array([len(a) for a, b in pairs], np.uint8)
     lb = np.array([len(b) for a, b in pairs], np.uint8)
     ta = np.vstack([oracle.encode_title(a) for a, b in pairs])
