@@ -437,7 +437,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps):
-        total_ms = 0.0
+        step_ms = []
         result = None
         for _ in range(steps):
             flush.zero_()
@@ -447,12 +447,14 @@ def run_ours(args):
             result = fn()
             stop.record()
             stop.synchronize()
-            total_ms += start.elapsed_time(stop)
+            step_ms.append(start.elapsed_time(stop))
         barrier()
-        t = torch.tensor([total_ms], dtype=torch.float64, device=device)
+        # every step starts at a barrier, so a step lasts as long as its slowest rank: max over ranks PER STEP, then the sum
+        # (the max of the ranks' sums would hide the steps in which different ranks were the slow one)
+        t = torch.tensor(step_ms if step_ms else [0.0], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), result
+        return float(t.sum().item()), result
 
     for _ in range(args.warmup):
         step_device()
